@@ -1,0 +1,159 @@
+/*
+ * shrimpy_b200 -- C-ABI of the B200-native light-sheet deskew / affine resample.
+ *
+ * The reference (czbiohub-sf/shrimPy) is pure Python and has no FFI of its own:
+ * the boundary this library replaces is the set of Python call sites into the
+ * un-vendored `biahub` package:
+ *
+ *   shrimpy/preprocessing.py:226-231   biahub.deskew.get_deskewed_data_shape
+ *   shrimpy/preprocessing.py:408-413   biahub.deskew.fast_deskew_zyx
+ *   scripts/measure_psf.py:230-246     biahub.analysis.deskew.{get_deskewed_data_shape,deskew_data}
+ *
+ * Every entry point below names the reference call it stands behind.  The
+ * signatures carry plain pointers and sizes only (no torch types); the Python
+ * host layer (shrimpy_b200/_cabi.py) binds them with ctypes, see INTEGRATION.md.
+ *
+ * Conventions
+ *   - raw stack  raw[z, y, x], shape (Z, Y, X): axis 0 scan, axis 1 tilt,
+ *     axis 2 coverslip (scripts/measure_psf.py:91,101).
+ *   - deskewed   out[p, o1, o2], shape (ceil(Y/n), X, Xp), float32.
+ *   - all device-level calls are asynchronous on the given stream, allocate
+ *     nothing and never synchronise; they are thread-safe for distinct
+ *     streams/buffers.
+ *   - return value: 0 on success, otherwise a SHRIMPY_E* code; a human-readable
+ *     message is available from shrimpy_last_error() (thread-local).
+ */
+#ifndef SHRIMPY_B200_H
+#define SHRIMPY_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SHRIMPY_B200_ABI_VERSION 1
+
+enum {
+    SHRIMPY_OK = 0,
+    SHRIMPY_EINVAL = 1,   /* bad argument (shape, dtype, stride, alignment)   */
+    SHRIMPY_ECUDA = 2,    /* a CUDA runtime / driver call failed                */
+    SHRIMPY_ENOGPU = 3,   /* no sm_100 device visible                           */
+    SHRIMPY_ENOMEM = 4    /* device or pinned-host allocation failed            */
+};
+
+enum {
+    SHRIMPY_U16 = 0,      /* camera frames as acquired (mantis.yaml:8 "16bit") */
+    SHRIMPY_F32 = 1       /* what shrimpy/preprocessing.py:316 hands over today */
+};
+
+/* Kernel selection for the deskew; AUTO picks TMA when strides/alignment allow. */
+enum {
+    SHRIMPY_KERNEL_AUTO = 0,
+    SHRIMPY_KERNEL_DIRECT = 1, /* plain gather, any shape/stride/alignment       */
+    SHRIMPY_KERNEL_TMA = 2     /* TMA-staged smem tiles, 128-bit smem reads      */
+};
+
+int shrimpy_abi_version(void);
+const char *shrimpy_last_error(void);
+
+/*
+ * Geometry of the deskew (replaces biahub.deskew.get_deskewed_data_shape,
+ * called at shrimpy/preprocessing.py:228-231 and scripts/measure_psf.py:230-234).
+ *   out_shape[3]  = (ceil(Y/n), X, Xp)
+ *   voxel_size[3] = (n*sin(theta)*pixel_size_um, pixel_size_um, pixel_size_um)
+ *   row0[3]       = (M00, M02, Z_shift) of the output->input affine row that
+ *                   maps (o0, o2) to the scan coordinate:
+ *                   z_in = (Z_shift + o0*M00) + o2*M02
+ * All arithmetic in float64, libm cos/sin.
+ */
+int shrimpy_deskew_geometry(int Z, int Y, int X, double ls_angle_deg, double px_to_scan_ratio,
+                            int keep_overhang, int average_n_slices, double pixel_size_um,
+                            int64_t out_shape[3], double voxel_size[3], double row0[3]);
+
+/*
+ * Device-resident deskew of one stack (replaces the body of
+ * biahub.deskew.fast_deskew_zyx, called at shrimpy/preprocessing.py:408-413;
+ * also absorbs the uint16->float32 convert of preprocessing.py:316 when
+ * raw_dtype == SHRIMPY_U16).
+ *
+ *   d_raw      device pointer, element (z,y,x) at d_raw[z*raw_stride_z + y*raw_stride_y + x]
+ *   d_out      device pointer, element (p,o1,o2) at d_out[p*out_stride_p + o1*out_stride_1 + o2]
+ *   strides    in ELEMENTS; pass 0 for the contiguous default
+ *   m00,m02,shift   row0 from shrimpy_deskew_geometry (or the host's own float64 values)
+ *   n_avg      average_n_slices (edge-replicated when Y % n_avg != 0)
+ *   cval       value written where z_in < 0 or z_in > Z-1 (strict)
+ *   kernel     SHRIMPY_KERNEL_*
+ *   stream     cudaStream_t (NULL = legacy default stream)
+ */
+int shrimpy_deskew_device(const void *d_raw, int raw_dtype, float *d_out, int Z, int Y, int X, int Xp,
+                          int n_avg, double m00, double m02, double shift, float cval,
+                          int64_t raw_stride_z, int64_t raw_stride_y, int64_t out_stride_p,
+                          int64_t out_stride_1, int kernel, void *stream);
+
+/*
+ * Windowed form of the same kernel: computes out[p_begin:p_begin+p_count, :, c_begin:c_begin+c_count]
+ * from a raw SLAB that holds only rows y in [y_origin, y_origin+y_count) and scan slices
+ * z in [z_origin, z_origin+z_count) of the full (Z,Y,X) stack.  Geometry (Z, Y, Xp, the
+ * affine row) always refers to the FULL stack, so every voxel is bit-identical to the
+ * un-windowed call.  Used by the host pipeline (tilt slabs, halo-free), by tilt/column
+ * sharding across GPUs, and by the scan-axis split with halo.
+ *   d_raw  element (z,y,x) at d_raw[(z-z_origin)*raw_stride_z + (y-y_origin)*raw_stride_y + x]
+ *   d_out  element (p,o1,o2) at d_out[(p-p_begin)*out_stride_p + o1*out_stride_1 + (o2-c_begin)]
+ * The slab must contain every row/slice the window needs; otherwise SHRIMPY_EINVAL.
+ * shrimpy_deskew_window_needs() reports that range.
+ */
+typedef struct shrimpy_window {
+    int32_t p_begin, p_count; /* tilt blocks (output axis 0)       */
+    int32_t c_begin, c_count; /* output columns (output axis 2)    */
+    int32_t y_origin, y_count; /* raw tilt rows present in d_raw   */
+    int32_t z_origin, z_count; /* raw scan slices present in d_raw */
+} shrimpy_window;
+
+int shrimpy_deskew_window_needs(int Z, int Y, int n_avg, double m00, double m02, double shift, int p_begin,
+                                int p_count, int c_begin, int c_count, int32_t y_range[2], int32_t z_range[2]);
+
+int shrimpy_deskew_window_device(const void *d_raw, int raw_dtype, float *d_out, int Z, int Y, int X, int Xp,
+                                 int n_avg, double m00, double m02, double shift, float cval,
+                                 int64_t raw_stride_z, int64_t raw_stride_y, int64_t out_stride_p,
+                                 int64_t out_stride_1, const shrimpy_window *window, int kernel, void *stream);
+
+/*
+ * Device-resident trilinear resample with a 3x4 (row-major, 12 doubles)
+ * output-index -> input-index matrix in ZYX voxel units (the registration
+ * resample named by BASELINE.json configs[2]; upstream
+ * biahub apply_affine_transform(method="scipy") == scipy.ndimage.affine_transform
+ * (order=1, mode="constant")).  NaN inputs are read as 0 when nan_to_zero != 0.
+ */
+int shrimpy_affine_device(const float *d_in, float *d_out, int iz, int iy, int ix, int oz, int oy, int ox,
+                          const double M[12], float cval, int nan_to_zero, void *stream);
+
+/* min over a device array (for cval = min(raw), the scipy-generation default). */
+int shrimpy_min_device(const void *d_raw, int raw_dtype, int64_t count, float *d_result, void *stream);
+
+/*
+ * Host-buffer deskew (replaces biahub.analysis.deskew.deskew_data as called at
+ * scripts/measure_psf.py:239-246: numpy in, numpy out).  The stack is cut into
+ * tilt slabs (multiples of n_avg rows, halo-free: SURVEY.md 8e) that are
+ * streamed H2D -> kernel -> D2H on three streams with double-buffered device
+ * slabs.  h_raw / h_out may be pageable; pinned (cudaHostRegister'd or
+ * cudaHostAlloc'd) buffers make the copies truly asynchronous.
+ * Synchronous: returns when h_out is complete.
+ */
+typedef struct shrimpy_pipeline shrimpy_pipeline;
+
+int shrimpy_pipeline_create(int device, size_t device_bytes_budget, shrimpy_pipeline **out);
+void shrimpy_pipeline_destroy(shrimpy_pipeline *p);
+int shrimpy_deskew_host(shrimpy_pipeline *p, const void *h_raw, int raw_dtype, float *h_out, int Z, int Y,
+                        int X, int Xp, int n_avg, double m00, double m02, double shift, float cval);
+/* counters of the last shrimpy_deskew_host call: kernels launched, H2D / D2H bytes */
+int shrimpy_pipeline_stats(const shrimpy_pipeline *p, int64_t *launches, int64_t *h2d_bytes, int64_t *d2h_bytes);
+
+/* Number of kernel launches issued by this library in this process (all entry points). */
+int64_t shrimpy_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SHRIMPY_B200_H */

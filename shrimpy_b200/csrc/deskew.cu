@@ -1,0 +1,463 @@
+// Light-sheet deskew kernels for sm_100a.
+//
+// out[p, o1, o2] = mean_{k<n} lerp_z(raw[:, Y-1-o0_k, X-1-o1], z_in(o0_k, o2)),
+//   o0_k = min(n*p + k, Y-1),  z_in = (shift + o0*m00) + o2*m02   (float64, no FMA),
+//   outside (z_in < 0 or z_in > Z-1, strict)  ->  cval.
+// This is the closed form of scipy.ndimage.affine_transform(order=1, mode="constant")
+// followed by the edge-padded block mean, i.e. what biahub's deskew computes for
+// shrimpy/preprocessing.py:408-413 and scripts/measure_psf.py:239-246.
+//
+// Two kernels:
+//   deskew_direct_kernel  one thread per output voxel, plain global gathers; any shape,
+//                         stride and alignment.  Correctness fallback.
+//   deskew_tma_kernel     one CTA per (tilt block p, 128-byte raw-x tile, o2 tile).  The n raw
+//                         tilt rows of the tile are staged in shared memory by TMA as
+//                         [scan slice][128 B of x] boxes with the 128-byte swizzle; each thread
+//                         owns one output column o2 (so its scan index and lerp weight are
+//                         computed once, in float64) and walks the x tile with 128-bit shared
+//                         loads; a warp's 32 lanes write 32 consecutive o2 -> coalesced 128-byte
+//                         global stores.  The read is coalesced along raw x, the write along o2:
+//                         the (z,x) -> (x,o2) transpose happens in shared memory.
+#include "common.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+
+namespace shrimpy {
+
+struct DeskewParams {
+    const void *raw;
+    float *out;
+    int Z, Y, X, Xp, n;        // geometry of the FULL stack
+    int p0, pcount;            // window: tilt blocks
+    int cbeg, cend;            // window: output columns [cbeg, cend)
+    int y_org, y_cnt;          // raw rows held by the slab
+    int z_org, z_cnt;          // raw scan slices held by the slab
+    long long raw_sz, raw_sy;  // element strides of raw
+    long long out_sp, out_s1;  // element strides of out
+    double m00, m02, shift;
+    float cval;
+    float inv_n;
+    int T2;        // o2 extent of a tile (32, 64, 128 or 256)
+    int nz_cap;    // scan slices per staged row (multiple of 8, <= 256)
+    int tiles_x;   // number of raw-x tiles
+    int tiles_o2;  // number of o2 tiles
+};
+
+// acc / n, correctly rounded for small integer n (q = acc*(1/n) followed by one FMA residual
+// correction); for n a power of two the correction is exactly zero.
+__device__ __forceinline__ float block_mean(float acc, float nf, float inv_n) {
+    const float q = acc * inv_n;
+    const float r = fmaf(-nf, q, acc);
+    return fmaf(r, inv_n, q);
+}
+
+__device__ __forceinline__ double scan_coord(double base, int o2, double m02) {
+    // scipy accumulates shift + o0*M00 first, then + o2*M02, each product and sum rounded separately.
+    return __dadd_rn(base, __dmul_rn((double)o2, m02));
+}
+
+template <typename T>
+__global__ void __launch_bounds__(128) deskew_direct_kernel(const DeskewParams P) {
+    const int o2 = P.cbeg + (blockIdx.x % P.tiles_o2) * blockDim.x + threadIdx.x;
+    const int o1 = blockIdx.x / P.tiles_o2;
+    const int p = P.p0 + blockIdx.y;
+    if (o2 >= P.cend) return;
+    const T *__restrict__ raw = static_cast<const T *>(P.raw);
+    const long long xoff = P.X - 1 - o1;
+    const double zmax = (double)(P.Z - 1);
+    float acc = 0.f;
+    for (int k = 0; k < P.n; ++k) {
+        const int o0 = min(P.n * p + k, P.Y - 1);
+        const long long yoff = (long long)(P.Y - 1 - o0 - P.y_org) * P.raw_sy;
+        const double base = __dadd_rn(P.shift, __dmul_rn((double)o0, P.m00));
+        const double z = scan_coord(base, o2, P.m02);
+        float v = P.cval;
+        if (z >= 0.0 && z <= zmax) {
+            const double fz = floor(z);
+            const float w = (float)(z - fz);
+            const int z0 = (int)fz;
+            const int z1 = min(z0 + 1, P.Z - 1);
+            const float a = (float)__ldg(raw + (long long)(z0 - P.z_org) * P.raw_sz + yoff + xoff);
+            const float b = (float)__ldg(raw + (long long)(z1 - P.z_org) * P.raw_sz + yoff + xoff);
+            v = fmaf(w, b - a, a);
+        }
+        acc = (k == 0) ? v : acc + v;
+    }
+    if (P.n > 1) acc = block_mean(acc, (float)P.n, P.inv_n);
+    __stcs(P.out + (long long)(p - P.p0) * P.out_sp + (long long)o1 * P.out_s1 + (o2 - P.cbeg), acc);
+}
+
+// ---- TMA-staged kernel -------------------------------------------------------
+
+template <typename T>
+struct Chunk;  // 16 bytes of raw-x held in a uint4
+
+template <>
+struct Chunk<uint16_t> {
+    static constexpr int kElems = 8;
+    static __device__ __forceinline__ float get(const uint4 &v, int j) {
+        const uint32_t word = (j < 2) ? v.x : (j < 4) ? v.y : (j < 6) ? v.z : v.w;
+        return (float)((j & 1) ? (word >> 16) : (word & 0xffffu));
+    }
+};
+
+template <>
+struct Chunk<float> {
+    static constexpr int kElems = 4;
+    static __device__ __forceinline__ float get(const uint4 &v, int j) {
+        return __uint_as_float(j == 0 ? v.x : j == 1 ? v.y : j == 2 ? v.z : v.w);
+    }
+};
+
+constexpr int kTmaThreads = 256;
+constexpr int kRowBytes = 128;  // one staged row = 128 B of raw x = one swizzle span
+constexpr int kMaxTmaAvg = 4;   // template instantiations exist for n = 1..4
+
+template <typename T, int NAVG>
+__global__ void __launch_bounds__(kTmaThreads, 3)
+    deskew_tma_kernel(const __grid_constant__ CUtensorMap tmap, const DeskewParams P) {
+    constexpr int EPC = Chunk<T>::kElems;
+    constexpr int TX = 8 * EPC;
+
+    extern __shared__ uint8_t smem_dyn[];
+    __shared__ __align__(8) uint64_t bar;
+
+    // The 128-byte swizzle wants 1024-byte aligned tiles.
+    const uint32_t pad = (1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u;
+    const uint8_t *tile = smem_dyn + pad;
+    const uint32_t region_bytes = (uint32_t)P.nz_cap * kRowBytes;
+
+    const int tx = blockIdx.x % P.tiles_x;
+    const int t2 = blockIdx.x / P.tiles_x;
+    const int p = P.p0 + blockIdx.y;
+    const int x0 = tx * TX;
+    const int c0 = P.cbeg + t2 * P.T2;
+    const int c_last = min(c0 + P.T2, P.cend) - 1;
+    const double zmax = (double)(P.Z - 1);
+
+    // Scan range this tile needs from each of its n tilt rows.  Pure function of the block
+    // index, so every thread derives the same values; rounding is monotone in o2, hence the
+    // tile's first/last columns bound every thread's coordinate.
+    double base[NAVG];
+    int zlo[NAVG];
+    bool need[NAVG];
+    bool any_need = false;
+#pragma unroll
+    for (int k = 0; k < NAVG; ++k) {
+        const int o0 = min(NAVG * p + k, P.Y - 1);
+        base[k] = __dadd_rn(P.shift, __dmul_rn((double)o0, P.m00));
+        const double zfirst = scan_coord(base[k], c0, P.m02);
+        const double zlast = scan_coord(base[k], c_last, P.m02);
+        need[k] = !(zlast < 0.0 || zfirst > zmax);
+        zlo[k] = (int)floor(fmin(fmax(zfirst, 0.0), zmax));
+        any_need |= need[k];
+    }
+
+    if (threadIdx.x == 0 && any_need) {
+        mbar_init(&bar, 1);
+        fence_mbar_init();
+        uint32_t bytes = 0;
+#pragma unroll
+        for (int k = 0; k < NAVG; ++k) bytes += need[k] ? region_bytes : 0u;
+        mbar_arrive_expect_tx(&bar, bytes);
+#pragma unroll
+        for (int k = 0; k < NAVG; ++k) {
+            if (need[k]) {
+                const int o0 = min(NAVG * p + k, P.Y - 1);
+                tma_load_3d(smem_u32(tile) + k * region_bytes, &tmap, x0, P.Y - 1 - o0 - P.y_org,
+                            zlo[k] - P.z_org, &bar);
+            }
+        }
+    }
+
+    // Per-thread column state while the boxes are in flight.
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warps_o2 = P.T2 >> 5;           // 1, 2, 4 or 8
+    const int parts = 8 / warps_o2;           // how many warps share one o2 span, splitting the x chunks
+    const int part = warp / warps_o2;
+    const int o2 = c0 + (warp % warps_o2) * 32 + lane;
+    const bool col_ok = o2 < P.cend;
+
+    float w[NAVG];
+    uint32_t off0[NAVG], off1[NAVG];  // byte offset of the two tap rows inside the tile
+    uint32_t sw0[NAVG], sw1[NAVG];    // their swizzle keys ((row & 7) << 4)
+    bool inside[NAVG];
+#pragma unroll
+    for (int k = 0; k < NAVG; ++k) {
+        const double z = scan_coord(base[k], o2, P.m02);
+        inside[k] = col_ok && z >= 0.0 && z <= zmax;
+        const double zc = inside[k] ? z : (double)zlo[k];
+        const double fz = floor(zc);
+        w[k] = (float)(zc - fz);
+        const int z0 = (int)fz;
+        const int r0 = min(z0 - zlo[k], P.nz_cap - 1);
+        const int r1 = min(min(z0 + 1, P.Z - 1) - zlo[k], P.nz_cap - 1);
+        off0[k] = k * region_bytes + (uint32_t)r0 * kRowBytes;
+        off1[k] = k * region_bytes + (uint32_t)r1 * kRowBytes;
+        sw0[k] = ((uint32_t)r0 & 7u) << 4;
+        sw1[k] = ((uint32_t)r1 & 7u) << 4;
+    }
+
+    __syncthreads();  // barrier init visible to every waiter
+    if (any_need) mbar_wait(&bar, 0);
+
+    const float nf = (float)NAVG;
+    float *out_col = P.out + (long long)(p - P.p0) * P.out_sp + (o2 - P.cbeg);
+
+    for (int c = part; c < 8; c += parts) {
+        float acc[EPC];
+#pragma unroll
+        for (int k = 0; k < NAVG; ++k) {
+            float v[EPC];
+            if (inside[k]) {
+                const uint4 A = *reinterpret_cast<const uint4 *>(tile + off0[k] + (((uint32_t)c << 4) ^ sw0[k]));
+                const uint4 B = *reinterpret_cast<const uint4 *>(tile + off1[k] + (((uint32_t)c << 4) ^ sw1[k]));
+#pragma unroll
+                for (int j = 0; j < EPC; ++j) {
+                    const float a = Chunk<T>::get(A, j);
+                    const float b = Chunk<T>::get(B, j);
+                    v[j] = fmaf(w[k], b - a, a);
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < EPC; ++j) v[j] = P.cval;
+            }
+#pragma unroll
+            for (int j = 0; j < EPC; ++j) acc[j] = (k == 0) ? v[j] : acc[j] + v[j];
+        }
+        if (col_ok) {
+#pragma unroll
+            for (int j = 0; j < EPC; ++j) {
+                const int x = x0 + c * EPC + j;
+                if (x < P.X) {
+                    const float r = (NAVG > 1) ? block_mean(acc[j], nf, P.inv_n) : acc[j];
+                    __stcs(out_col + (long long)(P.X - 1 - x) * P.out_s1, r);
+                }
+            }
+        }
+    }
+}
+
+// ---- host side -----------------------------------------------------------------
+
+static int env_int(const char *name, int fallback) {
+    const char *s = getenv(name);
+    return (s && *s) ? atoi(s) : fallback;
+}
+
+template <typename T>
+static int launch_direct(const DeskewParams &Pin, cudaStream_t stream) {
+    DeskewParams P = Pin;
+    const int threads = 128;
+    P.tiles_o2 = (P.cend - P.cbeg + threads - 1) / threads;
+    const long long gx = (long long)P.tiles_o2 * P.X;
+    if (gx > 2147483647LL || P.pcount > 65535)
+        return fail(SHRIMPY_EINVAL, "deskew: volume too large for the direct kernel grid (%lld x %d)", gx, P.pcount);
+    deskew_direct_kernel<T><<<dim3((unsigned)gx, (unsigned)P.pcount), threads, 0, stream>>>(P);
+    count_launch();
+    SHRIMPY_CUDA_TRY(cudaGetLastError());
+    return SHRIMPY_OK;
+}
+
+template <typename T, int NAVG>
+static int launch_tma_n(const CUtensorMap &tmap, const DeskewParams &P, size_t smem, cudaStream_t stream) {
+    auto kern = deskew_tma_kernel<T, NAVG>;
+    if (smem > 48 * 1024)
+        SHRIMPY_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<dim3((unsigned)((long long)P.tiles_x * P.tiles_o2), (unsigned)P.pcount), kTmaThreads, smem, stream>>>(tmap, P);
+    count_launch();
+    SHRIMPY_CUDA_TRY(cudaGetLastError());
+    return SHRIMPY_OK;
+}
+
+// Returns SHRIMPY_OK and sets *used = true when the TMA kernel was launched; *used = false
+// (still SHRIMPY_OK) when the problem is not eligible and the caller should fall back.
+template <typename T>
+static int launch_tma(const DeskewParams &Pin, cudaStream_t stream, bool *used, bool required) {
+    *used = false;
+    DeskewParams P = Pin;
+    constexpr int ES = (int)sizeof(T);
+    constexpr int TX = 128 / ES;
+    const char *why = nullptr;
+    if (P.n > kMaxTmaAvg) why = "average_n_slices > 4";
+    else if (!(P.m02 > 0.0) || P.m00 > 0.0) why = "scan coordinate not monotone (need m02 > 0, m00 <= 0)";
+    else if ((reinterpret_cast<uintptr_t>(P.raw) & 15u) != 0) why = "raw pointer not 16-byte aligned";
+    else if ((P.raw_sy * ES) % 16 != 0 || (P.raw_sz * ES) % 16 != 0) why = "raw strides not multiples of 16 bytes";
+    else if (P.raw_sy < P.X || P.raw_sz < (long long)P.y_cnt * P.raw_sy) why = "raw strides overlap";
+    else if (P.pcount > 65535) why = "too many tilt blocks for grid.y";
+
+    if (!why) {
+        // Tile extent along o2: the staged scan range must fit nz_cap <= 256 slices and the CTA's
+        // shared memory; default 128 columns, overridable for experiments.
+        int T2 = env_int("SHRIMPY_DESKEW_T2", 128);
+        if (T2 != 32 && T2 != 64 && T2 != 128 && T2 != 256) T2 = 128;
+        const int smem_budget = env_int("SHRIMPY_DESKEW_SMEM", 72 * 1024);
+        for (;; T2 >>= 1) {
+            if (T2 < 32) {
+                why = "px_to_scan_ratio too large for a staged tile";
+                break;
+            }
+            const long long nz = (long long)std::ceil((T2 - 1) * P.m02) + 3;
+            const long long cap = (nz + 7) / 8 * 8;
+            if (cap <= 256 && cap * kRowBytes * P.n + 1024 <= smem_budget) {
+                P.T2 = T2;
+                P.nz_cap = (int)cap;
+                break;
+            }
+        }
+    }
+    if (why) {
+        if (required) return fail(SHRIMPY_EINVAL, "deskew: TMA kernel not applicable: %s", why);
+        return SHRIMPY_OK;
+    }
+    P.tiles_x = (P.X + TX - 1) / TX;
+    P.tiles_o2 = (P.cend - P.cbeg + P.T2 - 1) / P.T2;
+    if ((long long)P.tiles_x * P.tiles_o2 > 2147483647LL) {
+        if (required) return fail(SHRIMPY_EINVAL, "deskew: grid too large");
+        return SHRIMPY_OK;
+    }
+
+    EncodeTiledFn encode = tensor_map_encoder();
+    if (!encode) return fail(SHRIMPY_ECUDA, "cuTensorMapEncodeTiled is not available from the driver");
+    CUtensorMap tmap;
+    const cuuint64_t gdim[3] = {(cuuint64_t)P.X, (cuuint64_t)P.y_cnt, (cuuint64_t)P.z_cnt};
+    const cuuint64_t gstride[2] = {(cuuint64_t)P.raw_sy * ES, (cuuint64_t)P.raw_sz * ES};
+    const cuuint32_t box[3] = {(cuuint32_t)TX, 1u, (cuuint32_t)P.nz_cap};
+    const cuuint32_t estr[3] = {1u, 1u, 1u};
+    const CUresult rc = encode(&tmap, ES == 2 ? CU_TENSOR_MAP_DATA_TYPE_UINT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
+                               const_cast<void *>(P.raw), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (rc != CUDA_SUCCESS) {
+        if (required) return fail(SHRIMPY_ECUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)rc);
+        return SHRIMPY_OK;
+    }
+    const size_t smem = (size_t)P.nz_cap * kRowBytes * P.n + 1024;
+    int err;
+    switch (P.n) {
+        case 1: err = launch_tma_n<T, 1>(tmap, P, smem, stream); break;
+        case 2: err = launch_tma_n<T, 2>(tmap, P, smem, stream); break;
+        case 3: err = launch_tma_n<T, 3>(tmap, P, smem, stream); break;
+        default: err = launch_tma_n<T, 4>(tmap, P, smem, stream); break;
+    }
+    if (err == SHRIMPY_OK) *used = true;
+    return err;
+}
+
+template <typename T>
+static int deskew_dispatch(const DeskewParams &P, int kernel, cudaStream_t stream) {
+    if (kernel != SHRIMPY_KERNEL_DIRECT) {
+        bool used = false;
+        const int err = launch_tma<T>(P, stream, &used, kernel == SHRIMPY_KERNEL_TMA);
+        if (err != SHRIMPY_OK || used) return err;
+    }
+    return launch_direct<T>(P, stream);
+}
+
+}  // namespace shrimpy
+
+using namespace shrimpy;
+
+// Rows / slices of the full stack that a window touches (host mirror of the kernels' arithmetic).
+static void window_needs(int Z, int Y, int n, double m00, double m02, double shift, int p0, int pcount, int cbeg,
+                         int cend, int32_t y_range[2], int32_t z_range[2]) {
+    const int o0_first = std::min(n * p0, Y - 1);
+    const int o0_last = std::min(n * (p0 + pcount) - 1, Y - 1);
+    y_range[0] = Y - 1 - o0_last;
+    y_range[1] = Y - o0_first;  // exclusive
+    // z_in is increasing in o2 (m02 > 0) and non-increasing in o0 (m00 <= 0) for a light-sheet
+    // geometry; take the extremes over all four corners so odd signs stay safe.
+    double lo = INFINITY, hi = -INFINITY;
+    const int o0s[2] = {o0_first, o0_last};
+    const int cs[2] = {cbeg, cend - 1};
+    for (int a = 0; a < 2; ++a)
+        for (int b = 0; b < 2; ++b) {
+            volatile double t = (double)o0s[a] * m00;
+            volatile double base = shift + t;
+            volatile double u = (double)cs[b] * m02;
+            const double z = base + u;
+            lo = std::fmin(lo, z);
+            hi = std::fmax(hi, z);
+        }
+    if (hi < 0.0 || lo > (double)(Z - 1) || cend <= cbeg) {
+        z_range[0] = z_range[1] = 0;  // nothing inside
+        return;
+    }
+    z_range[0] = (int)std::floor(std::fmax(lo, 0.0));
+    z_range[1] = (int)std::fmin(std::floor(std::fmin(hi, (double)(Z - 1))) + 1.0, (double)(Z - 1)) + 1;  // exclusive
+}
+
+extern "C" int shrimpy_deskew_window_needs(int Z, int Y, int n_avg, double m00, double m02, double shift,
+                                           int p_begin, int p_count, int c_begin, int c_count, int32_t y_range[2],
+                                           int32_t z_range[2]) {
+    if (Z <= 0 || Y <= 0 || n_avg <= 0 || p_begin < 0 || p_count <= 0 || c_begin < 0 || c_count < 0 || !y_range ||
+        !z_range)
+        return fail(SHRIMPY_EINVAL, "window_needs: bad arguments");
+    if (p_begin + p_count > (Y + n_avg - 1) / n_avg) return fail(SHRIMPY_EINVAL, "window_needs: tilt blocks out of range");
+    window_needs(Z, Y, n_avg, m00, m02, shift, p_begin, p_count, c_begin, c_begin + c_count, y_range, z_range);
+    return SHRIMPY_OK;
+}
+
+extern "C" int shrimpy_deskew_window_device(const void *d_raw, int raw_dtype, float *d_out, int Z, int Y, int X,
+                                            int Xp, int n_avg, double m00, double m02, double shift, float cval,
+                                            int64_t raw_stride_z, int64_t raw_stride_y, int64_t out_stride_p,
+                                            int64_t out_stride_1, const shrimpy_window *win, int kernel,
+                                            void *stream) {
+    if (Z <= 0 || Y <= 0 || X <= 0 || Xp < 0 || n_avg <= 0)
+        return fail(SHRIMPY_EINVAL, "deskew: bad shape Z=%d Y=%d X=%d Xp=%d n=%d", Z, Y, X, Xp, n_avg);
+    if (raw_dtype != SHRIMPY_U16 && raw_dtype != SHRIMPY_F32)
+        return fail(SHRIMPY_EINVAL, "deskew: raw_dtype must be SHRIMPY_U16 or SHRIMPY_F32, got %d", raw_dtype);
+    if (kernel < SHRIMPY_KERNEL_AUTO || kernel > SHRIMPY_KERNEL_TMA)
+        return fail(SHRIMPY_EINVAL, "deskew: unknown kernel selector %d", kernel);
+    if (!std::isfinite(m00) || !std::isfinite(m02) || !std::isfinite(shift))
+        return fail(SHRIMPY_EINVAL, "deskew: non-finite affine row");
+    const int Yn = (Y + n_avg - 1) / n_avg;
+    shrimpy_window full = {0, Yn, 0, Xp, 0, Y, 0, Z};
+    const shrimpy_window &w = win ? *win : full;
+    if (w.p_begin < 0 || w.p_count < 0 || w.p_begin + w.p_count > Yn || w.c_begin < 0 || w.c_count < 0 ||
+        w.c_begin + w.c_count > Xp || w.y_origin < 0 || w.y_count <= 0 || w.y_origin + w.y_count > Y ||
+        w.z_origin < 0 || w.z_count <= 0 || w.z_origin + w.z_count > Z)
+        return fail(SHRIMPY_EINVAL, "deskew: window outside the stack");
+    if (w.p_count == 0 || w.c_count == 0) return SHRIMPY_OK;
+    if (!d_raw || !d_out) return fail(SHRIMPY_EINVAL, "deskew: null device pointer");
+
+    int32_t yr[2], zr[2];
+    window_needs(Z, Y, n_avg, m00, m02, shift, w.p_begin, w.p_count, w.c_begin, w.c_begin + w.c_count, yr, zr);
+    if (yr[0] < w.y_origin || yr[1] > w.y_origin + w.y_count)
+        return fail(SHRIMPY_EINVAL, "deskew: slab rows [%d,%d) do not cover the needed [%d,%d)", w.y_origin,
+                    w.y_origin + w.y_count, yr[0], yr[1]);
+    if (zr[1] > zr[0] && (zr[0] < w.z_origin || zr[1] > w.z_origin + w.z_count))
+        return fail(SHRIMPY_EINVAL, "deskew: slab slices [%d,%d) do not cover the needed [%d,%d)", w.z_origin,
+                    w.z_origin + w.z_count, zr[0], zr[1]);
+
+    DeskewParams P{};
+    P.raw = d_raw;
+    P.out = d_out;
+    P.Z = Z; P.Y = Y; P.X = X; P.Xp = Xp; P.n = n_avg;
+    P.p0 = w.p_begin; P.pcount = w.p_count;
+    P.cbeg = w.c_begin; P.cend = w.c_begin + w.c_count;
+    P.y_org = w.y_origin; P.y_cnt = w.y_count;
+    P.z_org = w.z_origin; P.z_cnt = w.z_count;
+    P.raw_sy = raw_stride_y ? raw_stride_y : X;
+    P.raw_sz = raw_stride_z ? raw_stride_z : (long long)w.y_count * P.raw_sy;
+    P.out_s1 = out_stride_1 ? out_stride_1 : w.c_count;
+    P.out_sp = out_stride_p ? out_stride_p : (long long)X * P.out_s1;
+    if (P.raw_sy < X || P.out_s1 < w.c_count)
+        return fail(SHRIMPY_EINVAL, "deskew: inner strides smaller than the row length");
+    P.m00 = m00; P.m02 = m02; P.shift = shift;
+    P.cval = cval;
+    P.inv_n = 1.0f / (float)n_avg;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    return raw_dtype == SHRIMPY_U16 ? deskew_dispatch<uint16_t>(P, kernel, s) : deskew_dispatch<float>(P, kernel, s);
+}
+
+extern "C" int shrimpy_deskew_device(const void *d_raw, int raw_dtype, float *d_out, int Z, int Y, int X, int Xp,
+                                     int n_avg, double m00, double m02, double shift, float cval,
+                                     int64_t raw_stride_z, int64_t raw_stride_y, int64_t out_stride_p,
+                                     int64_t out_stride_1, int kernel, void *stream) {
+    return shrimpy_deskew_window_device(d_raw, raw_dtype, d_out, Z, Y, X, Xp, n_avg, m00, m02, shift, cval,
+                                        raw_stride_z, raw_stride_y, out_stride_p, out_stride_1, nullptr, kernel,
+                                        stream);
+}

@@ -1,0 +1,161 @@
+// Host-buffer streaming pipeline: H2D slab -> deskew kernel -> D2H slab on three streams.
+//
+// Stands behind biahub.analysis.deskew.deskew_data as called at scripts/measure_psf.py:239-246
+// (numpy in, numpy out).  The reference script cuts the stack along raw X "so that it fits in
+// the GPU memory" (measure_psf.py:218-221); here the cut is along the tilt axis in multiples of
+// average_n_slices rows, which is just as halo-free and makes every output slab
+// one contiguous block of the result, so the D2H side is a single linear copy per slab.
+#include "common.cuh"
+
+#include <algorithm>
+#include <vector>
+
+struct shrimpy_pipeline {
+    int device = 0;
+    size_t budget = 0;
+    static constexpr int kBuf = 3;
+    cudaStream_t s_h2d = nullptr, s_run = nullptr, s_d2h = nullptr;
+    void *d_raw[kBuf] = {nullptr, nullptr, nullptr};
+    float *d_out[kBuf] = {nullptr, nullptr, nullptr};
+    size_t raw_cap = 0, out_cap = 0;
+    cudaEvent_t ev_h2d[kBuf], ev_run[kBuf], ev_d2h[kBuf];
+    bool events = false;
+    int64_t launches = 0, h2d_bytes = 0, d2h_bytes = 0;
+};
+
+using namespace shrimpy;
+
+static void pipeline_free_buffers(shrimpy_pipeline *p) {
+    for (int i = 0; i < shrimpy_pipeline::kBuf; ++i) {
+        if (p->d_raw[i]) cudaFree(p->d_raw[i]);
+        if (p->d_out[i]) cudaFree(p->d_out[i]);
+        p->d_raw[i] = nullptr;
+        p->d_out[i] = nullptr;
+    }
+    p->raw_cap = p->out_cap = 0;
+}
+
+extern "C" int shrimpy_pipeline_create(int device, size_t device_bytes_budget, shrimpy_pipeline **out) {
+    if (!out) return fail(SHRIMPY_EINVAL, "pipeline_create: null out");
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) return fail(SHRIMPY_ENOGPU, "no CUDA device visible");
+    if (device < 0 || device >= count) return fail(SHRIMPY_EINVAL, "pipeline_create: device %d of %d", device, count);
+    SHRIMPY_CUDA_TRY(cudaSetDevice(device));
+    shrimpy_pipeline *p = new shrimpy_pipeline();
+    p->device = device;
+    p->budget = device_bytes_budget ? device_bytes_budget : (size_t)2 << 30;
+    cudaError_t e = cudaStreamCreateWithFlags(&p->s_h2d, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&p->s_run, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&p->s_d2h, cudaStreamNonBlocking);
+    for (int i = 0; i < shrimpy_pipeline::kBuf && e == cudaSuccess; ++i) {
+        e = cudaEventCreateWithFlags(&p->ev_h2d[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_run[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_d2h[i], cudaEventDisableTiming);
+    }
+    if (e != cudaSuccess) {
+        delete p;
+        return fail(SHRIMPY_ECUDA, "pipeline_create: %s", cudaGetErrorString(e));
+    }
+    p->events = true;
+    *out = p;
+    return SHRIMPY_OK;
+}
+
+extern "C" void shrimpy_pipeline_destroy(shrimpy_pipeline *p) {
+    if (!p) return;
+    cudaSetDevice(p->device);
+    if (p->s_d2h) cudaStreamSynchronize(p->s_d2h);
+    pipeline_free_buffers(p);
+    if (p->events)
+        for (int i = 0; i < shrimpy_pipeline::kBuf; ++i) {
+            cudaEventDestroy(p->ev_h2d[i]);
+            cudaEventDestroy(p->ev_run[i]);
+            cudaEventDestroy(p->ev_d2h[i]);
+        }
+    if (p->s_h2d) cudaStreamDestroy(p->s_h2d);
+    if (p->s_run) cudaStreamDestroy(p->s_run);
+    if (p->s_d2h) cudaStreamDestroy(p->s_d2h);
+    delete p;
+}
+
+extern "C" int shrimpy_pipeline_stats(const shrimpy_pipeline *p, int64_t *launches, int64_t *h2d_bytes,
+                                      int64_t *d2h_bytes) {
+    if (!p) return fail(SHRIMPY_EINVAL, "pipeline_stats: null pipeline");
+    if (launches) *launches = p->launches;
+    if (h2d_bytes) *h2d_bytes = p->h2d_bytes;
+    if (d2h_bytes) *d2h_bytes = p->d2h_bytes;
+    return SHRIMPY_OK;
+}
+
+extern "C" int shrimpy_deskew_host(shrimpy_pipeline *p, const void *h_raw, int raw_dtype, float *h_out, int Z, int Y,
+                                   int X, int Xp, int n_avg, double m00, double m02, double shift, float cval) {
+    if (!p) return fail(SHRIMPY_EINVAL, "deskew_host: null pipeline");
+    if (Z <= 0 || Y <= 0 || X <= 0 || Xp < 0 || n_avg <= 0) return fail(SHRIMPY_EINVAL, "deskew_host: bad shape");
+    if (raw_dtype != SHRIMPY_U16 && raw_dtype != SHRIMPY_F32) return fail(SHRIMPY_EINVAL, "deskew_host: bad dtype");
+    p->launches = p->h2d_bytes = p->d2h_bytes = 0;
+    if (Xp == 0) return SHRIMPY_OK;
+    if (!h_raw || !h_out) return fail(SHRIMPY_EINVAL, "deskew_host: null host pointer");
+    SHRIMPY_CUDA_TRY(cudaSetDevice(p->device));
+
+    constexpr int kBuf = shrimpy_pipeline::kBuf;
+    const size_t es = raw_dtype == SHRIMPY_U16 ? 2 : 4;
+    const int Yn = (Y + n_avg - 1) / n_avg;
+    // bytes per tilt block: n raw rows in, one output plane out
+    const size_t raw_per_p = (size_t)Z * n_avg * X * es;
+    const size_t out_per_p = (size_t)X * Xp * sizeof(float);
+    // slab size: fits the budget with kBuf buffers in flight, and leaves >= ~12 slabs to overlap
+    size_t ps_budget = p->budget / (kBuf * (raw_per_p + out_per_p));
+    if (ps_budget == 0) ps_budget = 1;
+    int ps = (int)std::min<size_t>(ps_budget, (size_t)std::max(1, (Yn + 11) / 12));
+    const int n_slabs = (Yn + ps - 1) / ps;
+
+    const size_t raw_need = (size_t)ps * raw_per_p, out_need = (size_t)ps * out_per_p;
+    if (raw_need > p->raw_cap || out_need > p->out_cap) {
+        SHRIMPY_CUDA_TRY(cudaStreamSynchronize(p->s_d2h));
+        pipeline_free_buffers(p);
+        for (int i = 0; i < kBuf; ++i) {
+            SHRIMPY_CUDA_TRY(cudaMalloc(&p->d_raw[i], raw_need));
+            SHRIMPY_CUDA_TRY(cudaMalloc(reinterpret_cast<void **>(&p->d_out[i]), out_need));
+        }
+        p->raw_cap = raw_need;
+        p->out_cap = out_need;
+    }
+
+    const size_t src_pitch = (size_t)Y * X * es;  // one scan slice of the host stack
+    for (int i = 0; i < n_slabs; ++i) {
+        const int b = i % kBuf;
+        const int p0 = i * ps, pc = std::min(ps, Yn - p0);
+        int32_t yr[2], zr[2];
+        int rc = shrimpy_deskew_window_needs(Z, Y, n_avg, m00, m02, shift, p0, pc, 0, Xp, yr, zr);
+        if (rc) return rc;
+        const int yc = yr[1] - yr[0];
+        // H2D: Z pieces of (yc rows * X) contiguous elements, pitch = one full slice
+        if (i >= kBuf) SHRIMPY_CUDA_TRY(cudaStreamWaitEvent(p->s_h2d, p->ev_run[b], 0));  // slab i-kBuf consumed
+        const size_t width = (size_t)yc * X * es;
+        SHRIMPY_CUDA_TRY(cudaMemcpy2DAsync(p->d_raw[b], width,
+                                           static_cast<const char *>(h_raw) + (size_t)yr[0] * X * es, src_pitch,
+                                           width, (size_t)Z, cudaMemcpyHostToDevice, p->s_h2d));
+        SHRIMPY_CUDA_TRY(cudaEventRecord(p->ev_h2d[b], p->s_h2d));
+        p->h2d_bytes += (int64_t)(width * Z);
+
+        SHRIMPY_CUDA_TRY(cudaStreamWaitEvent(p->s_run, p->ev_h2d[b], 0));
+        if (i >= kBuf) SHRIMPY_CUDA_TRY(cudaStreamWaitEvent(p->s_run, p->ev_d2h[b], 0));  // out buffer drained
+        shrimpy_window w = {p0, pc, 0, Xp, yr[0], yc, 0, Z};
+        const int64_t before = shrimpy_launch_count();
+        rc = shrimpy_deskew_window_device(p->d_raw[b], raw_dtype, p->d_out[b], Z, Y, X, Xp, n_avg, m00, m02, shift,
+                                          cval, (int64_t)yc * X, X, (int64_t)X * Xp, Xp, &w, SHRIMPY_KERNEL_AUTO,
+                                          p->s_run);
+        if (rc) return rc;
+        p->launches += shrimpy_launch_count() - before;
+        SHRIMPY_CUDA_TRY(cudaEventRecord(p->ev_run[b], p->s_run));
+
+        SHRIMPY_CUDA_TRY(cudaStreamWaitEvent(p->s_d2h, p->ev_run[b], 0));
+        const size_t out_bytes = (size_t)pc * out_per_p;
+        SHRIMPY_CUDA_TRY(cudaMemcpyAsync(h_out + (size_t)p0 * X * Xp, p->d_out[b], out_bytes, cudaMemcpyDeviceToHost,
+                                         p->s_d2h));
+        SHRIMPY_CUDA_TRY(cudaEventRecord(p->ev_d2h[b], p->s_d2h));
+        p->d2h_bytes += (int64_t)out_bytes;
+    }
+    SHRIMPY_CUDA_TRY(cudaStreamSynchronize(p->s_d2h));
+    return SHRIMPY_OK;
+}

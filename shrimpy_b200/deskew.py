@@ -1,0 +1,334 @@
+"""Light-sheet deskew: the host side of the drop-in boundary.
+
+Mirrors the ``biahub`` names shrimPy imports:
+
+* ``get_deskewed_data_shape``  -- ``shrimpy/preprocessing.py:226-231``, ``scripts/measure_psf.py:230-234``
+* ``fast_deskew_zyx``          -- ``shrimpy/preprocessing.py:408-413`` (torch tensor in, tensor out, same device)
+* ``deskew_data``              -- ``scripts/measure_psf.py:239-246`` (numpy in, numpy out)
+
+Parameter NAMES are part of the contract: shrimPy selects keyword arguments by
+``inspect.signature`` (``shrimpy/preprocessing.py:44-56``), so a parameter with
+another name would be dropped silently.
+
+All arithmetic on voxels runs in the CUDA library behind the C-ABI
+(``include/shrimpy_b200.h``); this module only computes the float64 geometry,
+allocates through torch and passes raw pointers plus the current stream.
+There is no CPU or PyTorch fallback.
+"""
+
+from __future__ import annotations
+
+import ctypes
+import math
+from dataclasses import dataclass
+from typing import Optional, Sequence, Tuple, Union
+
+import numpy as np
+
+from . import _cabi
+
+__all__ = [
+    "DeskewGeometry",
+    "deskew_geometry",
+    "get_deskewed_data_shape",
+    "fast_deskew_zyx",
+    "deskew_zyx",
+    "deskew_data",
+    "deskew_window",
+    "window_needs",
+    "HostPipeline",
+]
+
+
+@dataclass(frozen=True)
+class DeskewGeometry:
+    """Float64 geometry of one deskew: shapes plus the affine row mapping (o0, o2) to scan index."""
+
+    raw_shape: Tuple[int, int, int]
+    out_shape: Tuple[int, int, int]       # (ceil(Y/n), X, Xp)
+    voxel_size: Tuple[float, float, float]
+    n_avg: int
+    m00: float                            # -r*cos(theta)
+    m02: float                            # r
+    shift: float                          # Z_shift (0 with keep_overhang)
+
+    @property
+    def unaveraged_shape(self) -> Tuple[int, int, int]:
+        return (self.raw_shape[1], self.raw_shape[2], self.out_shape[2])
+
+    def matrix(self) -> np.ndarray:
+        """4x4 output-index -> input-index matrix (scipy convention) of the un-averaged resample."""
+        _, Y, X = self.raw_shape
+        return np.array([[self.m00, 0.0, self.m02, self.shift],
+                         [-1.0, 0.0, 0.0, Y - 1.0],
+                         [0.0, -1.0, 0.0, X - 1.0],
+                         [0.0, 0.0, 0.0, 1.0]])
+
+    @property
+    def algorithmic_bytes(self) -> Tuple[int, int]:
+        """(input voxels, output voxels) -- every input read once, every output written once."""
+        return (int(np.prod(self.raw_shape)), int(np.prod(self.out_shape)))
+
+
+def deskew_geometry(raw_data_shape: Sequence[int], ls_angle_deg: float, px_to_scan_ratio: float,
+                    keep_overhang: bool, average_n_slices: int = 1, pixel_size_um: float = 1) -> DeskewGeometry:
+    """All scalar geometry in float64, with numpy's ``cos``/``sin`` like the upstream Python.
+
+    Xp = ceil(Z/r + Y cos(theta)) with the overhang kept, ceil(Z/r - Y cos(theta)) without;
+    Z_shift = 0 resp. floor(Y cos(theta) r)  (SURVEY.md section 8 a2/a4).
+    """
+    if len(raw_data_shape) != 3:
+        raise ValueError(f"raw_data_shape must be (Z, Y, X), got {tuple(raw_data_shape)}")
+    Z, Y, X = (int(s) for s in raw_data_shape)
+    n = int(average_n_slices)
+    if min(Z, Y, X) <= 0 or n <= 0:
+        raise ValueError(f"non-positive size in raw_data_shape={tuple(raw_data_shape)} / average_n_slices={n}")
+    if not px_to_scan_ratio > 0:
+        raise ValueError("px_to_scan_ratio must be positive")
+    theta = ls_angle_deg * np.pi / 180
+    sin_t, cos_t = np.sin(theta), np.cos(theta)
+    overhang = Y * cos_t
+    extent = Z / px_to_scan_ratio
+    Xp = int(np.ceil(extent + overhang)) if keep_overhang else int(np.ceil(extent - overhang))
+    shift = 0 if keep_overhang else int(np.floor(Y * cos_t * px_to_scan_ratio))
+    return DeskewGeometry(
+        raw_shape=(Z, Y, X),
+        out_shape=(-(-Y // n), X, max(Xp, 0)),
+        voxel_size=(n * sin_t * pixel_size_um, pixel_size_um, pixel_size_um),
+        n_avg=n,
+        m00=float(-px_to_scan_ratio * cos_t),
+        m02=float(px_to_scan_ratio),
+        shift=float(shift),
+    )
+
+
+def get_deskewed_data_shape(raw_data_shape: Sequence[int], ls_angle_deg: float, px_to_scan_ratio: float,
+                            keep_overhang: bool, average_n_slices: int = 1, pixel_size_um: float = 1):
+    """``(deskewed_shape_zyx, voxel_size_zyx)`` -- see :func:`deskew_geometry`."""
+    g = deskew_geometry(raw_data_shape, ls_angle_deg, px_to_scan_ratio, keep_overhang, average_n_slices,
+                        pixel_size_um)
+    return g.out_shape, g.voxel_size
+
+
+# ---------------------------------------------------------------------------------------------
+# device path (torch tensors)
+# ---------------------------------------------------------------------------------------------
+
+def _torch():
+    import torch
+
+    return torch
+
+
+def _require_cuda(torch, device=None):
+    if not torch.cuda.is_available():
+        raise RuntimeError("shrimpy_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+    dev = torch.device("cuda" if device is None else device)
+    if dev.type != "cuda":
+        raise RuntimeError(f"shrimpy_b200 computes on CUDA devices only, got device={device!r}; "
+                           "there is no CPU fallback")
+    if dev.index is None:
+        dev = torch.device("cuda", torch.cuda.current_device())
+    return dev
+
+
+def _device_dtype(torch, t):
+    """Map a tensor dtype to (C-ABI dtype code, tensor in a supported dtype)."""
+    if t.dtype == torch.uint16:
+        return _cabi.U16, t
+    if t.dtype == torch.float32:
+        return _cabi.F32, t
+    return _cabi.F32, t.to(torch.float32)   # same cast shrimpy/preprocessing.py:316 applies
+
+
+def _resolve_cval(torch, raw, code, cval, stream) -> float:
+    if cval is not None:
+        return float(cval)
+    # scipy-generation default: pad with min(raw); reduced on the device
+    slot = torch.empty(1, dtype=torch.float32, device=raw.device)
+    _cabi.check(_cabi.lib().shrimpy_min_device(raw.data_ptr(), code, raw.numel(), slot.data_ptr(), stream))
+    return float(slot.item())
+
+
+def deskew_zyx(raw_data, ls_angle_deg: float, px_to_scan_ratio: float, keep_overhang: bool,
+               average_n_slices: int = 1, cval: Optional[float] = 0.0, out=None, kernel: str = "auto"):
+    """Deskew a CUDA tensor ``(Z, Y, X)`` (uint16 or float32) into float32 ``(ceil(Y/n), X, Xp)``.
+
+    Runs asynchronously on torch's current stream; ``out`` may be a preallocated
+    contiguous float32 tensor of the deskewed shape.
+    """
+    torch = _torch()
+    if raw_data.dim() != 3:
+        raise ValueError(f"raw_data must be (Z, Y, X), got shape {tuple(raw_data.shape)}")
+    if raw_data.device.type != "cuda":
+        raise RuntimeError("deskew_zyx expects a CUDA tensor")
+    g = deskew_geometry(tuple(raw_data.shape), ls_angle_deg, px_to_scan_ratio, keep_overhang, average_n_slices)
+    code, raw = _device_dtype(torch, raw_data)
+    if raw.stride(2) != 1 or raw.numel() == 0:
+        raw = raw.contiguous()
+    with torch.cuda.device(raw.device):
+        stream = torch.cuda.current_stream().cuda_stream
+        if out is None:
+            out = torch.empty(g.out_shape, dtype=torch.float32, device=raw.device)
+        elif (tuple(out.shape) != g.out_shape or out.dtype != torch.float32 or not out.is_contiguous()
+              or out.device != raw.device):
+            raise ValueError(f"out must be a contiguous float32 tensor of shape {g.out_shape} on {raw.device}")
+        if out.numel() == 0:
+            return out
+        fill = _resolve_cval(torch, raw, code, cval, stream)
+        Z, Y, X = g.raw_shape
+        _cabi.check(_cabi.lib().shrimpy_deskew_device(
+            raw.data_ptr(), code, out.data_ptr(), Z, Y, X, g.out_shape[2], g.n_avg, g.m00, g.m02, g.shift, fill,
+            raw.stride(0), raw.stride(1), 0, 0, _cabi.KERNELS[kernel], stream))
+    return out
+
+
+def fast_deskew_zyx(raw_data, ls_angle_deg: float, px_to_scan_ratio: float, keep_overhang: bool,
+                    average_n_slices: int = 1, cval: Optional[float] = 0.0):
+    """Drop-in for ``biahub.deskew.fast_deskew_zyx`` (``shrimpy/preprocessing.py:408-413``).
+
+    The result lives on the input's device.  A CUDA tensor is processed in place
+    on the current stream; a CPU tensor is streamed through the GPU with the host
+    pipeline and comes back as a CPU tensor (the arithmetic never runs on the CPU).
+    """
+    torch = _torch()
+    if not isinstance(raw_data, torch.Tensor):
+        raise TypeError("fast_deskew_zyx expects a torch.Tensor; use deskew_data for numpy arrays")
+    if raw_data.device.type == "cuda":
+        return deskew_zyx(raw_data, ls_angle_deg, px_to_scan_ratio, keep_overhang, average_n_slices, cval)
+    if raw_data.device.type != "cpu":
+        raise RuntimeError(f"unsupported device {raw_data.device}")
+    host = raw_data.detach()
+    if host.dtype not in (torch.uint16, torch.float32):
+        host = host.to(torch.float32)
+    result = deskew_data(host.contiguous().numpy(), ls_angle_deg, px_to_scan_ratio, keep_overhang,
+                         average_n_slices, cval=cval)
+    return torch.from_numpy(result)
+
+
+def window_needs(g: DeskewGeometry, p_begin: int, p_count: int, c_begin: int, c_count: int):
+    """Raw rows ``[y0, y1)`` and scan slices ``[z0, z1)`` that an output window reads."""
+    yr = (ctypes.c_int32 * 2)()
+    zr = (ctypes.c_int32 * 2)()
+    Z, Y, _ = g.raw_shape
+    _cabi.check(_cabi.lib().shrimpy_deskew_window_needs(Z, Y, g.n_avg, g.m00, g.m02, g.shift, p_begin, p_count,
+                                                        c_begin, c_count, yr, zr))
+    return (int(yr[0]), int(yr[1])), (int(zr[0]), int(zr[1]))
+
+
+def deskew_window(raw_slab, g: DeskewGeometry, *, p_begin: int, p_count: int, c_begin: int, c_count: int,
+                  y_origin: int, z_origin: int, cval: float = 0.0, out=None, kernel: str = "auto"):
+    """Deskew one output window from a raw slab (CUDA tensor holding rows/slices from the origins on).
+
+    Returns ``out[p_begin:p_begin+p_count, :, c_begin:c_begin+c_count]`` as a compact tensor;
+    geometry ``g`` is that of the FULL stack so the voxels equal the un-windowed result bit for bit.
+    """
+    torch = _torch()
+    code, raw = _device_dtype(torch, raw_slab)
+    if raw.stride(2) != 1:
+        raw = raw.contiguous()
+    Z, Y, X = g.raw_shape
+    if raw.shape[2] != X:
+        raise ValueError("slab must span the full raw X axis")
+    with torch.cuda.device(raw.device):
+        stream = torch.cuda.current_stream().cuda_stream
+        if out is None:
+            out = torch.empty((p_count, X, c_count), dtype=torch.float32, device=raw.device)
+        win = _cabi.Window(p_begin, p_count, c_begin, c_count, y_origin, raw.shape[1], z_origin, raw.shape[0])
+        _cabi.check(_cabi.lib().shrimpy_deskew_window_device(
+            raw.data_ptr(), code, out.data_ptr(), Z, Y, X, g.out_shape[2], g.n_avg, g.m00, g.m02, g.shift,
+            float(cval), raw.stride(0), raw.stride(1), out.stride(0), out.stride(1), ctypes.byref(win),
+            _cabi.KERNELS[kernel], stream))
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# host path (numpy arrays)
+# ---------------------------------------------------------------------------------------------
+
+class HostPipeline:
+    """Owner of one ``shrimpy_pipeline`` (three streams + device slab buffers on one GPU)."""
+
+    def __init__(self, device: int = 0, device_bytes_budget: int = 0):
+        handle = ctypes.c_void_p()
+        _cabi.check(_cabi.lib().shrimpy_pipeline_create(int(device), int(device_bytes_budget), ctypes.byref(handle)))
+        self._handle = handle
+        self.device = int(device)
+
+    def close(self) -> None:
+        if self._handle:
+            _cabi.lib().shrimpy_pipeline_destroy(self._handle)
+            self._handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def stats(self) -> dict:
+        a, b, c = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int64()
+        _cabi.check(_cabi.lib().shrimpy_pipeline_stats(self._handle, ctypes.byref(a), ctypes.byref(b),
+                                                       ctypes.byref(c)))
+        return {"launches": a.value, "h2d_bytes": b.value, "d2h_bytes": c.value}
+
+    def deskew(self, raw: np.ndarray, g: DeskewGeometry, cval: float, out: Optional[np.ndarray] = None) -> np.ndarray:
+        """``raw`` C-contiguous uint16/float32 ``(Z,Y,X)``; ``out`` C-contiguous float32 of ``g.out_shape``."""
+        if raw.dtype == np.uint16:
+            code = _cabi.U16
+        elif raw.dtype == np.float32:
+            code = _cabi.F32
+        else:
+            raise TypeError(f"host deskew takes uint16 or float32, got {raw.dtype}")
+        if not raw.flags.c_contiguous or tuple(raw.shape) != g.raw_shape:
+            raise ValueError("raw must be C-contiguous with the geometry's shape")
+        if out is None:
+            out = np.empty(g.out_shape, dtype=np.float32)
+        elif out.dtype != np.float32 or not out.flags.c_contiguous or tuple(out.shape) != g.out_shape:
+            raise ValueError(f"out must be C-contiguous float32 of shape {g.out_shape}")
+        Z, Y, X = g.raw_shape
+        _cabi.check(_cabi.lib().shrimpy_deskew_host(
+            self._handle, raw.ctypes.data, code, out.ctypes.data, Z, Y, X, g.out_shape[2], g.n_avg,
+            g.m00, g.m02, g.shift, float(cval)))
+        return out
+
+
+_pipelines: dict = {}
+
+
+def _pipeline_for(index: int) -> HostPipeline:
+    pipe = _pipelines.get(index)
+    if pipe is None:
+        pipe = _pipelines[index] = HostPipeline(index)
+    return pipe
+
+
+def deskew_data(raw_data: np.ndarray, ls_angle_deg: float, px_to_scan_ratio: float, keep_overhang: bool,
+                average_n_slices: int = 1, device: Union[str, int, None] = "cuda", cval: Optional[float] = 0.0,
+                out: Optional[np.ndarray] = None) -> np.ndarray:
+    """Drop-in for ``biahub.analysis.deskew.deskew_data`` (``scripts/measure_psf.py:239-246``).
+
+    numpy ``(Z, Y, X)`` in, float32 numpy ``(ceil(Y/n), X, Xp)`` out.  uint16 and
+    float32 stacks are streamed as they are; any other dtype is cast to float32
+    first (what ``shrimpy/preprocessing.py:316`` does).  ``cval=None`` pads with
+    ``min(raw)`` (the scipy-generation default), otherwise with ``cval``.
+    """
+    torch = _torch()
+    dev = _require_cuda(torch, device if not isinstance(device, int) else f"cuda:{device}")
+    raw = np.asarray(raw_data)
+    if raw.ndim != 3:
+        raise ValueError(f"raw_data must be (Z, Y, X), got shape {raw.shape}")
+    if raw.dtype not in (np.uint16, np.float32):
+        raw = raw.astype(np.float32)
+    raw = np.ascontiguousarray(raw)
+    g = deskew_geometry(raw.shape, ls_angle_deg, px_to_scan_ratio, keep_overhang, average_n_slices)
+    if math.prod(g.out_shape) == 0:
+        return np.empty(g.out_shape, dtype=np.float32)
+    fill = float(raw.min()) if cval is None else float(cval)
+    return _pipeline_for(dev.index).deskew(raw, g, fill, out)
