@@ -1,0 +1,119 @@
+"""GPU parity of the affine registration resample against the scipy oracle."""
+
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from helpers import CONTRACT_TOL, assert_close_range
+
+pytestmark = pytest.mark.gpu
+GOLDEN = Path(__file__).parent / "golden"
+AFFINE_TOL = 3e-6   # three nested float32 lerps vs scipy's float64 weights
+
+
+@pytest.fixture(scope="module")
+def env():
+    import torch
+
+    from oracle import c_oracle, deskew_oracle
+    from shrimpy_b200 import register
+
+    return torch, register, deskew_oracle, c_oracle
+
+
+def _rot(a, b, c):
+    a, b, c = np.deg2rad([a, b, c])
+    Rz = np.array([[1, 0, 0], [0, np.cos(a), -np.sin(a)], [0, np.sin(a), np.cos(a)]])
+    Ry = np.array([[np.cos(b), 0, np.sin(b)], [0, 1, 0], [-np.sin(b), 0, np.cos(b)]])
+    Rx = np.array([[np.cos(c), -np.sin(c), 0], [np.sin(c), np.cos(c), 0], [0, 0, 1]])
+    return Rz @ Ry @ Rx
+
+
+def _run(env, vol, M, shape, **kw):
+    torch, register, _, _ = env
+    out = register.affine_transform_zyx(torch.from_numpy(vol).cuda(), M, shape, **kw)
+    torch.cuda.synchronize()
+    return out.cpu().numpy()
+
+
+def test_golden_vectors(env):
+    data = np.load(GOLDEN / "deskew_small.npz")
+    vol = data["affine_general__vol"]
+    for tag in ("general", "rot90"):
+        M, want = data[f"affine_{tag}__matrix"], data[f"affine_{tag}__out"]
+        got = _run(env, vol, M, want.shape)
+        rel = assert_close_range(got, want, AFFINE_TOL, tag)
+        assert rel <= CONTRACT_TOL
+        assert np.array_equal(got == 0.0, want == 0.0)
+
+
+@pytest.mark.parametrize("shape_in,shape_out", [((20, 64, 80), (20, 64, 80)), ((11, 33, 47), (13, 50, 129)),
+                                                  ((1, 5, 7), (1, 5, 7)), ((6, 40, 40), (0, 3, 3))])
+def test_general_matrix_matches_scipy(env, shape_in, shape_out):
+    _, _, o, _ = env
+    rng = np.random.default_rng(sum(shape_in))
+    vol = rng.standard_normal(shape_in).astype(np.float32)
+    M = np.eye(4)
+    M[:3, :3] = _rot(2.0, 1.0, 3.0) @ np.diag([1.03, 0.97, 1.1])
+    M[:3, 3] = [0.4, -1.2, 2.3]
+    want = o.apply_affine_transform(vol, M, shape_out, cval=-2.0)
+    got = _run(env, vol, M, shape_out, cval=-2.0)
+    assert got.shape == want.shape
+    if want.size:
+        assert_close_range(got, want, AFFINE_TOL, "general")
+        assert np.array_equal(got == -2.0, want == -2.0)
+
+
+def test_identity_and_integer_shift_are_exact(env):
+    rng = np.random.default_rng(5)
+    vol = rng.standard_normal((9, 31, 37)).astype(np.float32)
+    assert np.array_equal(_run(env, vol, np.eye(4), vol.shape), vol)
+    M = np.eye(4)
+    M[:3, 3] = [1, -2, 3]
+    got = _run(env, vol, M, vol.shape, cval=9.0)
+    want = np.full_like(vol, 9.0)
+    want[:8, 2:, :34] = vol[1:, :29, 3:]
+    assert np.array_equal(got, want)
+
+
+def test_rot90_scale_onto_deskewed_grid(env):
+    """Mantis-like label-free -> fluorescence registration: in-plane 90 deg rotation x 1.288 + shift."""
+    _, _, o, c = env
+    rng = np.random.default_rng(6)
+    vol = rng.standard_normal((12, 96, 128)).astype(np.float32)
+    M = np.array([[1.0, 0, 0, 0.5], [0, 0, -1.288, 120.0], [0, 1.288, 0, -3.0], [0, 0, 0, 1]])
+    want = o.apply_affine_transform(vol, M, (10, 90, 70))
+    got = _run(env, vol, M, (10, 90, 70))
+    assert_close_range(got, want, AFFINE_TOL, "rot90")
+    assert np.array_equal(got == 0.0, want == 0.0)
+
+
+def test_nan_to_num_and_numpy_front_end(env):
+    torch, register, o, _ = env
+    rng = np.random.default_rng(7)
+    vol = rng.standard_normal((5, 20, 24)).astype(np.float32)
+    vol[2, 3, 4] = np.nan
+    vol[1, 7, 9] = np.inf
+    M = np.eye(4)
+    M[:3, :3] = _rot(0.0, 0.0, 4.0)
+    want = o.apply_affine_transform(vol, M, vol.shape)
+    got = register.apply_affine_transform(vol, M, vol.shape)          # numpy in -> numpy out
+    assert isinstance(got, np.ndarray) and np.isfinite(got).all()
+    far = np.abs(want) < 1e30                                            # away from the FLT_MAX taps
+    assert np.max(np.abs(got[far] - want[far])) <= 1e-5
+    with pytest.raises(ValueError):
+        register.apply_affine_transform(vol, np.ones((4, 4)), vol.shape)
+
+
+def test_medium_volume_vs_c_oracle(env):
+    _, _, _, c = env
+    rng = np.random.default_rng(8)
+    vol = rng.standard_normal((24, 200, 256)).astype(np.float32)
+    M = np.eye(4)
+    M[:3, :3] = _rot(2.0, 1.0, 3.0) @ np.diag([1.03, 0.97, 1.1])
+    M[:3, 3] = [0.4, -1.2, 2.3]
+    want = c.apply_affine_transform(vol, M, vol.shape)
+    got = _run(env, vol, M, vol.shape)
+    assert_close_range(got, want, AFFINE_TOL, "medium")
+    assert np.array_equal(got == 0.0, want == 0.0)

@@ -1,0 +1,100 @@
+"""The C-ABI library loads on a CPU-only box and exports everything include/shrimpy_b200.h declares."""
+
+import ctypes
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import shrimpy_b200 as sb
+from shrimpy_b200 import _cabi
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def _declared_functions():
+    text = (ROOT / "include" / "shrimpy_b200.h").read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(shrimpy_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_every_declared_symbol_is_exported():
+    lib = _cabi.lib()
+    declared = _declared_functions()
+    assert len(declared) >= 12
+    assert set(declared) == set(_cabi.EXPORTS)
+    for name in declared:
+        assert hasattr(lib, name), name
+
+
+def test_abi_version_and_no_fallback_message():
+    assert _cabi.lib().shrimpy_abi_version() == 1
+    assert _cabi.launch_count() >= 0
+
+
+def test_c_geometry_matches_python():
+    lib = _cabi.lib()
+    rng = np.random.default_rng(1)
+    for _ in range(300):
+        Z, Y, X = (int(v) for v in rng.integers(1, 900, 3))
+        th, r = round(float(rng.uniform(1, 45)), 2), round(float(rng.uniform(0.2, 1.2)), 3)
+        keep, n = int(rng.integers(0, 2)), int(rng.integers(1, 5))
+        shape = (ctypes.c_int64 * 3)()
+        vox = (ctypes.c_double * 3)()
+        row = (ctypes.c_double * 3)()
+        assert lib.shrimpy_deskew_geometry(Z, Y, X, th, r, keep, n, 0.116, shape, vox, row) == 0
+        g = sb.deskew_geometry((Z, Y, X), th, r, bool(keep), n, 0.116)
+        assert tuple(shape) == g.out_shape
+        assert row[1] == g.m02 and row[2] == g.shift
+        assert row[0] == pytest.approx(g.m00, rel=1e-15)     # libm cos vs numpy cos: <= 1 ulp
+        assert tuple(vox) == pytest.approx(g.voxel_size, rel=1e-15)
+
+
+def test_argument_errors_surface_without_a_gpu():
+    lib = _cabi.lib()
+    rc = lib.shrimpy_deskew_device(None, 7, None, 4, 4, 4, 4, 1, -0.3, 0.39, 0.0, 0.0, 0, 0, 0, 0, 0, None)
+    assert rc == _cabi.EINVAL and b"raw_dtype" in lib.shrimpy_last_error()
+    rc = lib.shrimpy_deskew_device(None, 0, None, 0, 4, 4, 4, 1, -0.3, 0.39, 0.0, 0.0, 0, 0, 0, 0, 0, None)
+    assert rc == _cabi.EINVAL
+    with pytest.raises(_cabi.ShrimpyB200Error):
+        _cabi.check(rc)
+    yr = (ctypes.c_int32 * 2)()
+    zr = (ctypes.c_int32 * 2)()
+    assert lib.shrimpy_deskew_window_needs(600, 300, 3, -0.3377, 0.39, 101.0, 10, 5, 128, 256, yr, zr) == 0
+    assert (yr[0], yr[1]) == (300 - 45, 300 - 30)
+    assert 0 <= zr[0] < zr[1] <= 600
+
+
+def test_window_needs_cover_every_tap():
+    """Host mirror of the kernel arithmetic: the reported slab really contains every tap."""
+    g = sb.deskew_geometry((120, 31, 8), 30.0, 0.39, False, 3)
+    Yn, _, Xp = g.out_shape
+    for p0, pc, c0, cc in [(0, Yn, 0, Xp), (2, 3, 17, 40), (Yn - 1, 1, Xp - 5, 5), (0, 1, 0, 1)]:
+        (y0, y1), (z0, z1) = sb.window_needs(g, p0, pc, c0, cc)
+        o0 = np.arange(3 * p0, min(3 * (p0 + pc), 31))
+        assert y0 == 31 - 1 - o0.max() and y1 == 31 - o0.min()
+        z_in = (g.shift + o0[:, None] * g.m00) + np.arange(c0, c0 + cc)[None, :] * g.m02
+        inside = (z_in >= 0) & (z_in <= 119)
+        if inside.any():
+            lo = np.floor(z_in[inside]).min()
+            hi = np.minimum(np.floor(z_in[inside]) + 1, 119).max()
+            assert z0 <= lo and hi < z1
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    monkeypatch.setattr(_cabi, "_lib", None)
+    monkeypatch.setenv("SHRIMPY_B200_LIB", str(tmp_path / "nope.so"))
+    with pytest.raises(ImportError, match="no CPU or PyTorch fallback"):
+        _cabi.lib()
+
+
+def test_no_cpu_path():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("this test is about the CPU-only box")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        sb.deskew_data(np.zeros((4, 4, 8), np.uint16), 30.0, 0.39, True)
+    with pytest.raises(RuntimeError):
+        sb.fast_deskew_zyx(torch.zeros((4, 4, 8)), 30.0, 0.39, True)
