@@ -45,13 +45,12 @@ struct DeskewParams {
     int tiles_o2;  // number of o2 tiles
 };
 
-// acc / n, correctly rounded for small integer n (q = acc*(1/n) followed by one FMA residual
-// correction); for n a power of two the correction is exactly zero.
-__device__ __forceinline__ float block_mean(float acc, float nf, float inv_n) {
-    const float q = acc * inv_n;
-    const float r = fmaf(-nf, q, acc);
-    return fmaf(r, inv_n, q);
-}
+// Arithmetic shared by every kernel in this file (so that they agree bit for bit):
+//   d_k = b_k - a_k                      the two scan taps of tilt row k (exact for uint16 data)
+//   S   = ((a_0 + a_1) + a_2) ...        sequential; an outside row contributes cval, d_k = w_k = 0
+//   W   = fma(w_{n-1}, d_{n-1}, ... fma(w_1, d_1, w_0 * d_0))
+//   out = n == 1 ? fma(w_0, d_0, a_0) : (S + W) * (1/n);   every row outside -> exactly cval
+// For uint16 data S is an exact integer, so only W and the final scale round (float32).
 
 __device__ __forceinline__ double scan_coord(double base, int o2, double m02) {
     // scipy accumulates shift + o0*M00 first, then + o2*M02, each product and sum rounded separately.
@@ -67,47 +66,111 @@ __global__ void __launch_bounds__(128) deskew_direct_kernel(const DeskewParams P
     const T *__restrict__ raw = static_cast<const T *>(P.raw);
     const long long xoff = P.X - 1 - o1;
     const double zmax = (double)(P.Z - 1);
-    float acc = 0.f;
+    float S = 0.f, W = 0.f, one = P.cval;
+    int n_in = 0;
     for (int k = 0; k < P.n; ++k) {
         const int o0 = min(P.n * p + k, P.Y - 1);
         const long long yoff = (long long)(P.Y - 1 - o0 - P.y_org) * P.raw_sy;
         const double base = __dadd_rn(P.shift, __dmul_rn((double)o0, P.m00));
         const double z = scan_coord(base, o2, P.m02);
-        float v = P.cval;
+        float a = P.cval, d = 0.f, w = 0.f;
         if (z >= 0.0 && z <= zmax) {
             const double fz = floor(z);
-            const float w = (float)(z - fz);
+            w = (float)(z - fz);
             const int z0 = (int)fz;
             const int z1 = min(z0 + 1, P.Z - 1);
-            const float a = (float)__ldg(raw + (long long)(z0 - P.z_org) * P.raw_sz + yoff + xoff);
+            a = (float)__ldg(raw + (long long)(z0 - P.z_org) * P.raw_sz + yoff + xoff);
             const float b = (float)__ldg(raw + (long long)(z1 - P.z_org) * P.raw_sz + yoff + xoff);
-            v = fmaf(w, b - a, a);
+            d = b - a;
+            ++n_in;
         }
-        acc = (k == 0) ? v : acc + v;
+        S = (k == 0) ? a : S + a;
+        W = (k == 0) ? w * d : fmaf(w, d, W);
+        if (k == 0) one = fmaf(w, d, a);
     }
-    if (P.n > 1) acc = block_mean(acc, (float)P.n, P.inv_n);
-    __stcs(P.out + (long long)(p - P.p0) * P.out_sp + (long long)o1 * P.out_s1 + (o2 - P.cbeg), acc);
+    const float r = (n_in == 0) ? P.cval : (P.n == 1) ? one : (S + W) * P.inv_n;
+    __stcs(P.out + (long long)(p - P.p0) * P.out_sp + (long long)o1 * P.out_s1 + (o2 - P.cbeg), r);
 }
 
 // ---- TMA-staged kernel -------------------------------------------------------
 
 template <typename T>
-struct Chunk;  // 16 bytes of raw-x held in a uint4
+struct Chunk;  // 16 bytes of raw x held in a uint4
+
+__device__ __forceinline__ uint32_t word_of(const uint4 &v, int i) {
+    return i == 0 ? v.x : i == 1 ? v.y : i == 2 ? v.z : v.w;
+}
 
 template <>
 struct Chunk<uint16_t> {
     static constexpr int kElems = 8;
+    static constexpr uint32_t kMagic = 0x4B000000u;  // float 2^23: low mantissa bits hold an integer
     static __device__ __forceinline__ float get(const uint4 &v, int j) {
-        const uint32_t word = (j < 2) ? v.x : (j < 4) ? v.y : (j < 6) ? v.z : v.w;
+        const uint32_t word = word_of(v, j >> 1);
         return (float)((j & 1) ? (word >> 16) : (word & 0xffffu));
+    }
+    // uint16 -> bits of the float 2^23 + value with one byte permute (no integer->float convert)
+    static __device__ __forceinline__ uint32_t magic(const uint4 &v, int j) {
+        return __byte_perm(word_of(v, j >> 1), kMagic, (j & 1) ? 0x7632 : 0x7610);
+    }
+
+    // All n rows inside: S as an integer sum of the magic words (exact), W as an FMA chain.
+    template <int NAVG>
+    static __device__ __forceinline__ void fast(const uint8_t *tile, const uint32_t *off0, const uint32_t *off1,
+                                                const uint32_t *sw0, const uint32_t *sw1, const float *w,
+                                                uint32_t cbyte, float inv_n, float *out) {
+        uint32_t sum[kElems];
+        float W[kElems];
+#pragma unroll
+        for (int k = 0; k < NAVG; ++k) {
+            const uint4 A = *reinterpret_cast<const uint4 *>(tile + off0[k] + (cbyte ^ sw0[k]));
+            const uint4 B = *reinterpret_cast<const uint4 *>(tile + off1[k] + (cbyte ^ sw1[k]));
+#pragma unroll
+            for (int j = 0; j < kElems; ++j) {
+                const uint32_t am = magic(A, j), bm = magic(B, j);
+                const float d = __uint_as_float(bm) - __uint_as_float(am);  // exact: both are 2^23 + integer
+                if (NAVG == 1) {
+                    out[j] = fmaf(w[0], d, __uint_as_float(am) - 8388608.0f);
+                } else {
+                    sum[j] = (k == 0) ? am : sum[j] + am;
+                    W[j] = (k == 0) ? w[0] * d : fmaf(w[k], d, W[j]);
+                }
+            }
+        }
+        if (NAVG > 1) {
+#pragma unroll
+            for (int j = 0; j < kElems; ++j) {
+                const float S = __uint_as_float(sum[j] - (uint32_t)(NAVG - 1) * kMagic) - 8388608.0f;
+                out[j] = (S + W[j]) * inv_n;
+            }
+        }
     }
 };
 
 template <>
 struct Chunk<float> {
     static constexpr int kElems = 4;
-    static __device__ __forceinline__ float get(const uint4 &v, int j) {
-        return __uint_as_float(j == 0 ? v.x : j == 1 ? v.y : j == 2 ? v.z : v.w);
+    static __device__ __forceinline__ float get(const uint4 &v, int j) { return __uint_as_float(word_of(v, j)); }
+
+    template <int NAVG>
+    static __device__ __forceinline__ void fast(const uint8_t *tile, const uint32_t *off0, const uint32_t *off1,
+                                                const uint32_t *sw0, const uint32_t *sw1, const float *w,
+                                                uint32_t cbyte, float inv_n, float *out) {
+        float S[kElems], W[kElems], one[kElems];
+#pragma unroll
+        for (int k = 0; k < NAVG; ++k) {
+            const uint4 A = *reinterpret_cast<const uint4 *>(tile + off0[k] + (cbyte ^ sw0[k]));
+            const uint4 B = *reinterpret_cast<const uint4 *>(tile + off1[k] + (cbyte ^ sw1[k]));
+#pragma unroll
+            for (int j = 0; j < kElems; ++j) {
+                const float a = get(A, j), d = get(B, j) - a;
+                S[j] = (k == 0) ? a : S[j] + a;
+                W[j] = (k == 0) ? w[0] * d : fmaf(w[k], d, W[j]);
+                if (k == 0) one[j] = fmaf(w[0], d, a);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < kElems; ++j) out[j] = (NAVG == 1) ? one[j] : (S[j] + W[j]) * inv_n;
     }
 };
 
@@ -203,38 +266,57 @@ __global__ void __launch_bounds__(kTmaThreads, 3)
     __syncthreads();  // barrier init visible to every waiter
     if (any_need) mbar_wait(&bar, 0);
 
-    const float nf = (float)NAVG;
+    // Warp-uniform classification: the interior of the volume takes the branch-free fast path.
+    bool all_in = true, none_in = true;
+#pragma unroll
+    for (int k = 0; k < NAVG; ++k) {
+        all_in &= inside[k];
+        none_in &= !inside[k];
+    }
+    const bool warp_all_in = __all_sync(0xffffffffu, all_in);
+    const bool warp_none_in = __all_sync(0xffffffffu, none_in);
+
     float *out_col = P.out + (long long)(p - P.p0) * P.out_sp + (o2 - P.cbeg);
 
     for (int c = part; c < 8; c += parts) {
-        float acc[EPC];
+        float r[EPC];
+        if (warp_all_in) {
+            Chunk<T>::template fast<NAVG>(tile, off0, off1, sw0, sw1, w, (uint32_t)c << 4, P.inv_n, r);
+        } else if (warp_none_in) {
 #pragma unroll
-        for (int k = 0; k < NAVG; ++k) {
-            float v[EPC];
-            if (inside[k]) {
-                const uint4 A = *reinterpret_cast<const uint4 *>(tile + off0[k] + (((uint32_t)c << 4) ^ sw0[k]));
-                const uint4 B = *reinterpret_cast<const uint4 *>(tile + off1[k] + (((uint32_t)c << 4) ^ sw1[k]));
+            for (int j = 0; j < EPC; ++j) r[j] = P.cval;
+        } else {
+            // boundary warps: some rows / lanes outside
+            float S[EPC], W[EPC], one[EPC];
+#pragma unroll
+            for (int k = 0; k < NAVG; ++k) {
+                uint4 A = make_uint4(0, 0, 0, 0), B = A;
+                if (inside[k]) {
+                    A = *reinterpret_cast<const uint4 *>(tile + off0[k] + (((uint32_t)c << 4) ^ sw0[k]));
+                    B = *reinterpret_cast<const uint4 *>(tile + off1[k] + (((uint32_t)c << 4) ^ sw1[k]));
+                }
 #pragma unroll
                 for (int j = 0; j < EPC; ++j) {
-                    const float a = Chunk<T>::get(A, j);
-                    const float b = Chunk<T>::get(B, j);
-                    v[j] = fmaf(w[k], b - a, a);
+                    const float a = inside[k] ? Chunk<T>::get(A, j) : P.cval;
+                    const float d = inside[k] ? Chunk<T>::get(B, j) - a : 0.f;
+                    const float wk = inside[k] ? w[k] : 0.f;
+                    S[j] = (k == 0) ? a : S[j] + a;
+                    W[j] = (k == 0) ? wk * d : fmaf(wk, d, W[j]);
+                    if (k == 0) one[j] = fmaf(wk, d, a);
                 }
-            } else {
-#pragma unroll
-                for (int j = 0; j < EPC; ++j) v[j] = P.cval;
             }
 #pragma unroll
-            for (int j = 0; j < EPC; ++j) acc[j] = (k == 0) ? v[j] : acc[j] + v[j];
+            for (int j = 0; j < EPC; ++j)
+                r[j] = none_in ? P.cval : (NAVG == 1) ? one[j] : (S[j] + W[j]) * P.inv_n;
         }
         if (col_ok) {
+            const int xc = x0 + c * EPC;
+            const int xvalid = P.X - xc;  // elements of this chunk that exist
+            float *ptr = out_col + (long long)(P.X - 1 - xc) * P.out_s1;
 #pragma unroll
             for (int j = 0; j < EPC; ++j) {
-                const int x = x0 + c * EPC + j;
-                if (x < P.X) {
-                    const float r = (NAVG > 1) ? block_mean(acc[j], nf, P.inv_n) : acc[j];
-                    __stcs(out_col + (long long)(P.X - 1 - x) * P.out_s1, r);
-                }
+                if (j < xvalid) __stcs(ptr, r[j]);
+                ptr -= P.out_s1;
             }
         }
     }
@@ -291,8 +373,8 @@ static int launch_tma(const DeskewParams &Pin, cudaStream_t stream, bool *used, 
     if (!why) {
         // Tile extent along o2: the staged scan range must fit nz_cap <= 256 slices and the CTA's
         // shared memory; default 128 columns, overridable for experiments.
-        int T2 = env_int("SHRIMPY_DESKEW_T2", 128);
-        if (T2 != 32 && T2 != 64 && T2 != 128 && T2 != 256) T2 = 128;
+        int T2 = env_int("SHRIMPY_DESKEW_T2", 256);
+        if (T2 != 32 && T2 != 64 && T2 != 128 && T2 != 256) T2 = 256;
         const int smem_budget = env_int("SHRIMPY_DESKEW_SMEM", 72 * 1024);
         for (;; T2 >>= 1) {
             if (T2 < 32) {
