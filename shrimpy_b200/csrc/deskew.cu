@@ -48,8 +48,9 @@ struct DeskewParams {
 // Arithmetic shared by every kernel in this file (so that they agree bit for bit):
 //   d_k = b_k - a_k                      the two scan taps of tilt row k (exact for uint16 data)
 //   S   = ((a_0 + a_1) + a_2) ...        sequential; an outside row contributes cval, d_k = w_k = 0
-//   W   = fma(w_{n-1}, d_{n-1}, ... fma(w_1, d_1, w_0 * d_0))
-//   out = n == 1 ? fma(w_0, d_0, a_0) : (S + W) * (1/n);   every row outside -> exactly cval
+//   u_k = w_k * (1/n)                    lerp weight pre-scaled by the block-mean factor
+//   W   = fma(u_{n-1}, d_{n-1}, ... fma(u_1, d_1, u_0 * d_0))
+//   out = n == 1 ? fma(w_0, d_0, a_0) : fma(S, 1/n, W);   every row outside -> exactly cval
 // For uint16 data S is an exact integer, so only W and the final scale round (float32).
 
 __device__ __forceinline__ double scan_coord(double base, int o2, double m02) {
@@ -84,11 +85,12 @@ __global__ void __launch_bounds__(128) deskew_direct_kernel(const DeskewParams P
             d = b - a;
             ++n_in;
         }
+        const float u = w * P.inv_n;
         S = (k == 0) ? a : S + a;
-        W = (k == 0) ? w * d : fmaf(w, d, W);
+        W = (k == 0) ? u * d : fmaf(u, d, W);
         if (k == 0) one = fmaf(w, d, a);
     }
-    const float r = (n_in == 0) ? P.cval : (P.n == 1) ? one : (S + W) * P.inv_n;
+    const float r = (n_in == 0) ? P.cval : (P.n == 1) ? one : fmaf(S, P.inv_n, W);
     __stcs(P.out + (long long)(p - P.p0) * P.out_sp + (long long)o1 * P.out_s1 + (o2 - P.cbeg), r);
 }
 
@@ -118,7 +120,7 @@ struct Chunk<uint16_t> {
     template <int NAVG>
     static __device__ __forceinline__ void fast(const uint8_t *tile, const uint32_t *off0, const uint32_t *off1,
                                                 const uint32_t *sw0, const uint32_t *sw1, const float *w,
-                                                uint32_t cbyte, float inv_n, float *out) {
+                                                const float *u, uint32_t cbyte, float inv_n, float *out) {
         uint32_t sum[kElems];
         float W[kElems];
 #pragma unroll
@@ -133,7 +135,7 @@ struct Chunk<uint16_t> {
                     out[j] = fmaf(w[0], d, __uint_as_float(am) - 8388608.0f);
                 } else {
                     sum[j] = (k == 0) ? am : sum[j] + am;
-                    W[j] = (k == 0) ? w[0] * d : fmaf(w[k], d, W[j]);
+                    W[j] = (k == 0) ? u[0] * d : fmaf(u[k], d, W[j]);
                 }
             }
         }
@@ -141,7 +143,7 @@ struct Chunk<uint16_t> {
 #pragma unroll
             for (int j = 0; j < kElems; ++j) {
                 const float S = __uint_as_float(sum[j] - (uint32_t)(NAVG - 1) * kMagic) - 8388608.0f;
-                out[j] = (S + W[j]) * inv_n;
+                out[j] = fmaf(S, inv_n, W[j]);
             }
         }
     }
@@ -155,7 +157,7 @@ struct Chunk<float> {
     template <int NAVG>
     static __device__ __forceinline__ void fast(const uint8_t *tile, const uint32_t *off0, const uint32_t *off1,
                                                 const uint32_t *sw0, const uint32_t *sw1, const float *w,
-                                                uint32_t cbyte, float inv_n, float *out) {
+                                                const float *u, uint32_t cbyte, float inv_n, float *out) {
         float S[kElems], W[kElems], one[kElems];
 #pragma unroll
         for (int k = 0; k < NAVG; ++k) {
@@ -165,12 +167,12 @@ struct Chunk<float> {
             for (int j = 0; j < kElems; ++j) {
                 const float a = get(A, j), d = get(B, j) - a;
                 S[j] = (k == 0) ? a : S[j] + a;
-                W[j] = (k == 0) ? w[0] * d : fmaf(w[k], d, W[j]);
+                W[j] = (k == 0) ? u[0] * d : fmaf(u[k], d, W[j]);
                 if (k == 0) one[j] = fmaf(w[0], d, a);
             }
         }
 #pragma unroll
-        for (int j = 0; j < kElems; ++j) out[j] = (NAVG == 1) ? one[j] : (S[j] + W[j]) * inv_n;
+        for (int j = 0; j < kElems; ++j) out[j] = (NAVG == 1) ? one[j] : fmaf(S[j], inv_n, W[j]);
     }
 };
 
@@ -200,70 +202,70 @@ __global__ void __launch_bounds__(kTmaThreads, 3)
     const int c_last = min(c0 + P.T2, P.cend) - 1;
     const double zmax = (double)(P.Z - 1);
 
-    // Scan range this tile needs from each of its n tilt rows.  Pure function of the block
-    // index, so every thread derives the same values; rounding is monotone in o2, hence the
-    // tile's first/last columns bound every thread's coordinate.
-    double base[NAVG];
-    int zlo[NAVG];
-    bool need[NAVG];
-    bool any_need = false;
-#pragma unroll
-    for (int k = 0; k < NAVG; ++k) {
-        const int o0 = min(NAVG * p + k, P.Y - 1);
-        base[k] = __dadd_rn(P.shift, __dmul_rn((double)o0, P.m00));
-        const double zfirst = scan_coord(base[k], c0, P.m02);
-        const double zlast = scan_coord(base[k], c_last, P.m02);
-        need[k] = !(zlast < 0.0 || zfirst > zmax);
-        zlo[k] = (int)floor(fmin(fmax(zfirst, 0.0), zmax));
-        any_need |= need[k];
-    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-    if (threadIdx.x == 0 && any_need) {
-        mbar_init(&bar, 1);
-        fence_mbar_init();
-        uint32_t bytes = 0;
-#pragma unroll
-        for (int k = 0; k < NAVG; ++k) bytes += need[k] ? region_bytes : 0u;
-        mbar_arrive_expect_tx(&bar, bytes);
-#pragma unroll
-        for (int k = 0; k < NAVG; ++k) {
-            if (need[k]) {
-                const int o0 = min(NAVG * p + k, P.Y - 1);
-                tma_load_3d(smem_u32(tile) + k * region_bytes, &tmap, x0, P.Y - 1 - o0 - P.y_org,
-                            zlo[k] - P.z_org, &bar);
-            }
+    // Warp 0, lane k: scan range this tile needs from tilt row k (a pure function of the block
+    // index; rounding is monotone in o2, so the tile's first/last columns bound every thread's
+    // coordinate), then one TMA box per needed row.  The values are shared through smem.
+    __shared__ double s_base[NAVG];
+    __shared__ int s_zlo[NAVG];
+    __shared__ unsigned s_need;
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_init(&bar, 1);
+            fence_mbar_init();
         }
+        bool need = false;
+        int zlo = 0, yrow = 0;
+        if (lane < NAVG) {
+            const int o0 = min(NAVG * p + lane, P.Y - 1);
+            yrow = P.Y - 1 - o0 - P.y_org;
+            const double base = __dadd_rn(P.shift, __dmul_rn((double)o0, P.m00));
+            const double zfirst = scan_coord(base, c0, P.m02);
+            const double zlast = scan_coord(base, c_last, P.m02);
+            need = !(zlast < 0.0 || zfirst > zmax);
+            zlo = __double2int_rd(fmin(fmax(zfirst, 0.0), zmax));
+            s_base[lane] = base;
+            s_zlo[lane] = zlo;
+        }
+        const unsigned mask = __ballot_sync(0xffffffffu, need);
+        if (lane == 0) {
+            s_need = mask;
+            if (mask) mbar_arrive_expect_tx(&bar, (uint32_t)__popc(mask) * region_bytes);
+        }
+        __syncwarp();
+        if (need) tma_load_3d(smem_u32(tile) + lane * region_bytes, &tmap, x0, yrow, zlo - P.z_org, &bar);
     }
+    __syncthreads();  // row ranges and the initialised barrier visible to everyone
+    const bool any_need = s_need != 0;
 
     // Per-thread column state while the boxes are in flight.
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int warps_o2 = P.T2 >> 5;           // 1, 2, 4 or 8
     const int parts = 8 / warps_o2;           // how many warps share one o2 span, splitting the x chunks
     const int part = warp / warps_o2;
     const int o2 = c0 + (warp % warps_o2) * 32 + lane;
     const bool col_ok = o2 < P.cend;
 
-    float w[NAVG];
+    float w[NAVG], u[NAVG];           // lerp weight, and the same pre-scaled by 1/n
     uint32_t off0[NAVG], off1[NAVG];  // byte offset of the two tap rows inside the tile
     uint32_t sw0[NAVG], sw1[NAVG];    // their swizzle keys ((row & 7) << 4)
     bool inside[NAVG];
 #pragma unroll
     for (int k = 0; k < NAVG; ++k) {
-        const double z = scan_coord(base[k], o2, P.m02);
+        const int zlo = s_zlo[k];
+        const double z = scan_coord(s_base[k], o2, P.m02);
         inside[k] = col_ok && z >= 0.0 && z <= zmax;
-        const double zc = inside[k] ? z : (double)zlo[k];
-        const double fz = floor(zc);
-        w[k] = (float)(zc - fz);
-        const int z0 = (int)fz;
-        const int r0 = min(z0 - zlo[k], P.nz_cap - 1);
-        const int r1 = min(min(z0 + 1, P.Z - 1) - zlo[k], P.nz_cap - 1);
+        const int z0 = inside[k] ? __double2int_rd(z) : zlo;
+        w[k] = inside[k] ? (float)(z - (double)z0) : 0.f;
+        u[k] = w[k] * P.inv_n;
+        const int r0 = min(z0 - zlo, P.nz_cap - 1);
+        const int r1 = min(min(z0 + 1, P.Z - 1) - zlo, P.nz_cap - 1);
         off0[k] = k * region_bytes + (uint32_t)r0 * kRowBytes;
         off1[k] = k * region_bytes + (uint32_t)r1 * kRowBytes;
         sw0[k] = ((uint32_t)r0 & 7u) << 4;
         sw1[k] = ((uint32_t)r1 & 7u) << 4;
     }
 
-    __syncthreads();  // barrier init visible to every waiter
     if (any_need) mbar_wait(&bar, 0);
 
     // Warp-uniform classification: the interior of the volume takes the branch-free fast path.
@@ -276,12 +278,13 @@ __global__ void __launch_bounds__(kTmaThreads, 3)
     const bool warp_all_in = __all_sync(0xffffffffu, all_in);
     const bool warp_none_in = __all_sync(0xffffffffu, none_in);
 
-    float *out_col = P.out + (long long)(p - P.p0) * P.out_sp + (o2 - P.cbeg);
+    char *out_col = reinterpret_cast<char *>(P.out + (long long)(p - P.p0) * P.out_sp + (o2 - P.cbeg));
+    const long long row_bytes = P.out_s1 * (long long)sizeof(float);
 
     for (int c = part; c < 8; c += parts) {
         float r[EPC];
         if (warp_all_in) {
-            Chunk<T>::template fast<NAVG>(tile, off0, off1, sw0, sw1, w, (uint32_t)c << 4, P.inv_n, r);
+            Chunk<T>::template fast<NAVG>(tile, off0, off1, sw0, sw1, w, u, (uint32_t)c << 4, P.inv_n, r);
         } else if (warp_none_in) {
 #pragma unroll
             for (int j = 0; j < EPC; ++j) r[j] = P.cval;
@@ -299,24 +302,32 @@ __global__ void __launch_bounds__(kTmaThreads, 3)
                 for (int j = 0; j < EPC; ++j) {
                     const float a = inside[k] ? Chunk<T>::get(A, j) : P.cval;
                     const float d = inside[k] ? Chunk<T>::get(B, j) - a : 0.f;
-                    const float wk = inside[k] ? w[k] : 0.f;
                     S[j] = (k == 0) ? a : S[j] + a;
-                    W[j] = (k == 0) ? wk * d : fmaf(wk, d, W[j]);
-                    if (k == 0) one[j] = fmaf(wk, d, a);
+                    W[j] = (k == 0) ? u[k] * d : fmaf(u[k], d, W[j]);   // w = u = 0 outside
+                    if (k == 0) one[j] = fmaf(w[k], d, a);
                 }
             }
 #pragma unroll
             for (int j = 0; j < EPC; ++j)
-                r[j] = none_in ? P.cval : (NAVG == 1) ? one[j] : (S[j] + W[j]) * P.inv_n;
+                r[j] = none_in ? P.cval : (NAVG == 1) ? one[j] : fmaf(S[j], P.inv_n, W[j]);
         }
         if (col_ok) {
             const int xc = x0 + c * EPC;
-            const int xvalid = P.X - xc;  // elements of this chunk that exist
-            float *ptr = out_col + (long long)(P.X - 1 - xc) * P.out_s1;
+            const int xvalid = P.X - xc;  // elements of this chunk that exist (uniform over the CTA)
+            char *ptr = out_col + (long long)(P.X - 1 - xc) * row_bytes;
+            if (xvalid >= EPC) {
 #pragma unroll
-            for (int j = 0; j < EPC; ++j) {
-                if (j < xvalid) __stcs(ptr, r[j]);
-                ptr -= P.out_s1;
+                for (int j = 0; j < EPC; ++j) {
+                    __stcs(reinterpret_cast<float *>(ptr), r[j]);
+                    ptr -= row_bytes;
+                    asm volatile("" : "+l"(ptr));  // keep a stepped pointer (2 adds), not base+offset (4)
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < EPC; ++j) {
+                    if (j < xvalid) __stcs(reinterpret_cast<float *>(ptr), r[j]);
+                    ptr -= row_bytes;
+                }
             }
         }
     }
