@@ -4,13 +4,25 @@
 // (float64, products and sums rounded separately: scipy.ndimage.affine_transform's order),
 // outside (any c_a < 0 or c_a > dim_a - 1, strict) -> cval; order=1, mode="constant".
 //
-// affine_gather_kernel: each warp owns 32*kItems consecutive o2 of one output row, lane-major,
-// so global stores are coalesced; the (o0,o1) part of the coordinate is computed once per
-// thread in float64 and only one multiply-add per axis remains per voxel.  Input taps go
-// through the read-only path (L1/L2 absorb the 8-fold tap reuse).
+// Two kernels:
+//   affine_gather_kernel  one thread per output voxel, taps through the read-only global path.
+//                         Any matrix; used when the staged footprint of a tile would not fit.
+//   affine_tile_kernel    one CTA per output tile (TZ,TY,TX).  The input bounding box of the tile
+//                         (an affine image of a box is bounded by its 8 corners) is staged in
+//                         shared memory asynchronously: by ONE 3-D TMA box load when a warp's 32
+//                         consecutive o2 stay within a few input rows (near-identity transforms),
+//                         or by cp.async row copies at an ODD row pitch when lanes walk input y or z
+//                         (e.g. the in-plane 90 degree label-free -> fluorescence registration), so
+//                         the tap reads are bank-conflict-free either way.  Lanes own consecutive
+//                         o2 (coalesced stores); the 8 taps per voxel come from shared memory.
+//                         nan_to_num is applied lazily: a non-finite result (which every non-finite
+//                         tap produces) is recomputed from cleaned taps.  The host picks the tile
+//                         shape per matrix.
 #include "common.cuh"
 
+#include <algorithm>
 #include <cmath>
+#include <cstdlib>
 
 namespace shrimpy {
 
@@ -22,20 +34,47 @@ struct AffineParams {
     double M[12];
     float cval;
     int nan_to_zero;
-    int tiles_x;
+    int tiles_x;  // gather kernel: o2 tiles per row; tile kernel: tiles along o2
+    int tiles_y, tiles_z;
+    int TZ, TY, TX;         // output tile (tile kernel); TY is a power of two
+    int log2TY;
+    int BZ, BY, BX, pitch;  // staged input box and its odd row pitch (tile kernel)
+    unsigned tma_bytes;     // bytes one TMA box load delivers
 };
 
 constexpr int kAffThreads = 128;
 constexpr int kAffItems = 4;
+constexpr int kTileThreads = 256;
+
+// numpy.nan_to_num: nan -> 0, +-inf -> +-FLT_MAX
+__device__ __forceinline__ float clean(float v) {
+    const uint32_t b = __float_as_uint(v);
+    if ((b & 0x7f800000u) == 0x7f800000u) v = (b & 0x007fffffu) ? 0.f : __uint_as_float(b - 1u);
+    return v;
+}
 
 __device__ __forceinline__ float tap(const float *__restrict__ p, int nan_to_zero) {
-    float v = __ldg(p);
-    if (nan_to_zero) {
-        // numpy.nan_to_num: nan -> 0, +-inf -> +-FLT_MAX
-        if (v != v) v = 0.f;
-        else if (isinf(v)) v = copysignf(3.402823466e+38f, v);
-    }
-    return v;
+    const float v = __ldg(p);
+    return nan_to_zero ? clean(v) : v;
+}
+
+// One axis of the scipy coordinate: exact float64 value -> (floor, fraction), inside test.
+// c >= 0  <=>  floor >= 0;   c <= dim-1  <=>  floor < dim-1 or (floor == dim-1 and fraction == 0).
+__device__ __forceinline__ bool split_coord(double c, int dim, int &i0, float &w) {
+    i0 = __double2int_rd(c);
+    w = (float)(c - (double)i0);
+    return i0 >= 0 && (i0 < dim - 1 || (i0 == dim - 1 && w == 0.f && c == (double)i0));
+}
+
+// Interior fast path: floor and fraction of a coordinate without 64-bit conversions (F2I.F64,
+// I2F.F64 and F2F.F32.F64 issue at 1/8 rate).  Adding 1.5*2^29 with round-down leaves
+// floor(c * 2^23) + 2^51 in the mantissa: bits [22:0] of the low word are the fraction (23 bits,
+// truncated) and the bits above are floor(c) + 2^28.  Valid for |c| < 2^28 (checked on the host).
+__device__ __forceinline__ int split_fast(double c, float &w) {
+    const double s = __dadd_rd(c, 805306368.0);
+    const unsigned hi = (unsigned)__double2hiint(s), lo = (unsigned)__double2loint(s);
+    w = __uint_as_float((lo & 0x007fffffu) | 0x3f800000u) - 1.0f;
+    return (int)(__funnelshift_l(lo, hi, 9) - 0x90000000u);
 }
 
 __global__ void __launch_bounds__(kAffThreads) affine_gather_kernel(const AffineParams P) {
@@ -51,7 +90,6 @@ __global__ void __launch_bounds__(kAffThreads) affine_gather_kernel(const Affine
         const double t = __dadd_rn(P.M[4 * a + 3], __dmul_rn((double)o0, P.M[4 * a + 0]));
         base[a] = __dadd_rn(t, __dmul_rn((double)o1, P.M[4 * a + 1]));
     }
-    const double hz = (double)(P.iz - 1), hy = (double)(P.iy - 1), hx = (double)(P.ix - 1);
     const long long sz = (long long)P.iy * P.ix, sy = P.ix;
     float *row = P.out + ((long long)o0 * P.oy + o1) * P.ox;
 
@@ -59,14 +97,13 @@ __global__ void __launch_bounds__(kAffThreads) affine_gather_kernel(const Affine
     for (int i = 0; i < kAffItems; ++i) {
         const int o2 = col0 + 32 * i;
         if (o2 >= P.ox) break;
-        const double cz = __dadd_rn(base[0], __dmul_rn((double)o2, P.M[2]));
-        const double cy = __dadd_rn(base[1], __dmul_rn((double)o2, P.M[6]));
-        const double cx = __dadd_rn(base[2], __dmul_rn((double)o2, P.M[10]));
+        int z0, y0, x0;
+        float wz, wy, wx;
+        bool in = split_coord(__dadd_rn(base[0], __dmul_rn((double)o2, P.M[2])), P.iz, z0, wz);
+        in &= split_coord(__dadd_rn(base[1], __dmul_rn((double)o2, P.M[6])), P.iy, y0, wy);
+        in &= split_coord(__dadd_rn(base[2], __dmul_rn((double)o2, P.M[10])), P.ix, x0, wx);
         float r = P.cval;
-        if (cz >= 0.0 && cz <= hz && cy >= 0.0 && cy <= hy && cx >= 0.0 && cx <= hx) {
-            const double fz = floor(cz), fy = floor(cy), fx = floor(cx);
-            const float wz = (float)(cz - fz), wy = (float)(cy - fy), wx = (float)(cx - fx);
-            const int z0 = (int)fz, y0 = (int)fy, x0 = (int)fx;
+        if (in) {
             const int z1 = min(z0 + 1, P.iz - 1), y1 = min(y0 + 1, P.iy - 1), x1 = min(x0 + 1, P.ix - 1);
             const float *p00 = P.in + z0 * sz + y0 * sy;
             const float *p01 = P.in + z0 * sz + y1 * sy;
@@ -86,6 +123,216 @@ __global__ void __launch_bounds__(kAffThreads) affine_gather_kernel(const Affine
         }
         __stcs(row + o2, r);
     }
+}
+
+// ---- shared-memory tiled kernel ------------------------------------------------------------------
+
+__device__ __forceinline__ void cp_async4(uint32_t dst, const float *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+
+// Slow, fully general voxel: exact edge rule (c == dim-1 is inside, the second tap folds onto the
+// first there) and clamped box indices.  Only voxels on the rim of the input volume come here.
+struct EdgeCtx {
+    int iz, iy, ix;     // input dims
+    int BZ, BY, BX;     // staged box dims
+    int oz0, oy0, ox0;  // box origin
+    int pitch, zs;
+    float cval;
+    int clean;          // apply nan_to_num to the taps
+};
+
+__device__ __noinline__ float affine_edge_voxel(const float *box, EdgeCtx E, double cz, double cy, double cx) {
+    int z0, y0, x0;
+    float wz, wy, wx;
+    bool in = split_coord(cz, E.iz, z0, wz);
+    in &= split_coord(cy, E.iy, y0, wy);
+    in &= split_coord(cx, E.ix, x0, wx);
+    if (!in) return E.cval;
+    const int dz = (z0 + 1 < E.iz) ? E.zs : 0;
+    const int dy = (y0 + 1 < E.iy) ? E.pitch : 0;
+    const int dx = (x0 + 1 < E.ix) ? 1 : 0;
+    const int bz = min(max(z0 - E.oz0, 0), E.BZ - 1);
+    const int by = min(max(y0 - E.oy0, 0), E.BY - 1);
+    const int bx = min(max(x0 - E.ox0, 0), E.BX - 1);
+    const float *q = box + bz * E.zs + by * E.pitch + bx;
+    float v[8] = {q[0], q[dx], q[dy], q[dy + dx], q[dz], q[dz + dx], q[dz + dy], q[dz + dy + dx]};
+    if (E.clean) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = clean(v[i]);
+    }
+    const float a00 = fmaf(wx, v[1] - v[0], v[0]);
+    const float a01 = fmaf(wx, v[3] - v[2], v[2]);
+    const float a10 = fmaf(wx, v[5] - v[4], v[4]);
+    const float a11 = fmaf(wx, v[7] - v[6], v[6]);
+    const float b0 = fmaf(wy, a01 - a00, a00);
+    const float b1 = fmaf(wy, a11 - a10, a10);
+    return fmaf(wz, b1 - b0, b0);
+}
+
+// ITEMS = TX / 32 output columns per lane and tile row; CLEAN = nan_to_num semantics;
+// USE_TMA = stage the box with one TMA load (dense pitch) instead of cp.async rows (odd pitch).
+template <int ITEMS, bool CLEAN, bool USE_TMA>
+__global__ void __launch_bounds__(kTileThreads, 2)
+    affine_tile_kernel(const __grid_constant__ CUtensorMap tmap, const AffineParams P) {
+    extern __shared__ __align__(128) float box_raw[];
+    __shared__ int s_org[3];
+    __shared__ __align__(8) uint64_t bar;
+    // 128-byte aligned start, computed on the shared-window address so the loads stay LDS
+    float *box = box_raw + (((128u - (smem_u32(box_raw) & 127u)) & 127u) >> 2);
+
+    // z tiles fastest, then x, then y: neighbours that share a halo run close together in time,
+    // so halo re-reads are L2 hits and DRAM sees each input voxel about once.
+    const int tz = blockIdx.x % P.tiles_z;
+    const int tx = blockIdx.x / P.tiles_z;
+    const int ty = blockIdx.y;
+    const int t0z = tz * P.TZ, t0y = ty * P.TY, t0x = tx * (32 * ITEMS);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    // Box origin: floor of the minimum corner coordinate, per input axis.
+    if (threadIdx.x < 3) {
+        const int a = threadIdx.x;
+        const double e0 = (double)(min(t0z + P.TZ, P.oz) - 1 - t0z);
+        const double e1 = (double)(min(t0y + P.TY, P.oy) - 1 - t0y);
+        const double e2 = (double)(min(t0x + 32 * ITEMS, P.ox) - 1 - t0x);
+        const double m0 = P.M[4 * a + 0], m1 = P.M[4 * a + 1], m2 = P.M[4 * a + 2];
+        double lo = P.M[4 * a + 3] + t0z * m0 + t0y * m1 + t0x * m2;
+        lo += fmin(e0 * m0, 0.0) + fmin(e1 * m1, 0.0) + fmin(e2 * m2, 0.0);
+        const int dim = a == 0 ? P.iz : a == 1 ? P.iy : P.ix;
+        // clamp far-away tiles so the int conversion and the pointer arithmetic below stay defined
+        int org = __double2int_rd(fmin(fmax(lo - 1e-6, -4.0), (double)dim));
+        // TMA: the box must start on a 16-byte boundary of the innermost axis (an unaligned start
+        // raises an illegal-instruction fault on sm_100), so x is rounded down to 4 floats.
+        if (USE_TMA && a == 2) org &= ~3;
+        s_org[a] = org;
+    }
+    __syncthreads();
+    const int oz0 = s_org[0], oy0 = s_org[1], ox0 = s_org[2];
+    const int pitch = P.pitch;
+    const int zs = P.BY * pitch;
+
+    if (USE_TMA) {
+        // One box load; coordinates outside the volume are zero-filled and never read.
+        if (threadIdx.x == 0) {
+            mbar_init(&bar, 1);
+            fence_mbar_init();
+            mbar_arrive_expect_tx(&bar, P.tma_bytes);
+            tma_load_3d(smem_u32(box), &tmap, ox0, oy0, oz0, &bar);
+        }
+        __syncthreads();
+        mbar_wait(&bar, 0);
+    } else {
+        // One (z,y) row per warp iteration, lanes along x (coalesced), all copies in flight at once.
+        const int rows = P.BZ * P.BY;
+        const int lo = max(0, -ox0), hi = min(P.BX, P.ix - ox0);
+        const uint32_t box_s = smem_u32(box);
+        for (int r = warp; r < rows; r += kTileThreads / 32) {
+            const int bz = r / P.BY, by = r - bz * P.BY;
+            const int gz = oz0 + bz, gy = oy0 + by;
+            if ((unsigned)gz >= (unsigned)P.iz || (unsigned)gy >= (unsigned)P.iy) continue;
+            const float *src = P.in + ((long long)gz * P.iy + gy) * P.ix + ox0;
+            const int dst = r * pitch;
+#pragma unroll 4
+            for (int bx = lo + lane; bx < hi; bx += 32) cp_async4(box_s + 4u * (uint32_t)(dst + bx), src + bx);
+        }
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        __syncthreads();
+    }
+
+    // Resample: warp w takes tile rows (lz,ly) = w, w+8, ...; lanes own consecutive o2.
+    const int tile_rows = P.TZ << P.log2TY;
+    const int org_off = oz0 * zs + oy0 * pitch + ox0;
+    const unsigned hz = P.iz - 1, hy = P.iy - 1, hx = P.ix - 1;
+    const double m02 = P.M[2], m12 = P.M[6], m22 = P.M[10];
+    const int col = t0x + lane;
+    for (int r = warp; r < tile_rows; r += kTileThreads / 32) {
+        const int lz = r >> P.log2TY, ly = r & (P.TY - 1);
+        const int o0 = t0z + lz, o1 = t0y + ly;
+        if (o0 >= P.oz || o1 >= P.oy) continue;
+        double base[3];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const double t = __dadd_rn(P.M[4 * a + 3], __dmul_rn((double)o0, P.M[4 * a + 0]));
+            base[a] = __dadd_rn(t, __dmul_rn((double)o1, P.M[4 * a + 1]));
+        }
+        float *row = P.out + ((long long)o0 * P.oy + o1) * P.ox + col;
+#pragma unroll
+        for (int i = 0; i < ITEMS; ++i) {
+            const int o2 = col + 32 * i;
+            if (o2 < P.ox) {
+                const double cz = __dadd_rn(base[0], __dmul_rn((double)o2, m02));
+                const double cy = __dadd_rn(base[1], __dmul_rn((double)o2, m12));
+                const double cx = __dadd_rn(base[2], __dmul_rn((double)o2, m22));
+                float wz, wy, wx;
+                const int z0 = split_fast(cz, wz), y0 = split_fast(cy, wy), x0 = split_fast(cx, wx);
+                float res = 0.f;
+                bool rare = true;  // rim of the input volume, outside, or a non-finite tap
+                if ((unsigned)z0 < hz && (unsigned)y0 < hy && (unsigned)x0 < hx) {
+                    // interior: 0 <= c < dim-1 on every axis, both taps exist, no clamping needed
+                    const float *q = box + (z0 * zs + y0 * pitch + x0 - org_off);
+                    const float *q1 = q + pitch, *q2 = q + zs, *q3 = q2 + pitch;
+                    const float v000 = q[0], v001 = q[1], v010 = q1[0], v011 = q1[1];
+                    const float v100 = q2[0], v101 = q2[1], v110 = q3[0], v111 = q3[1];
+                    const float a00 = fmaf(wx, v001 - v000, v000);
+                    const float a01 = fmaf(wx, v011 - v010, v010);
+                    const float a10 = fmaf(wx, v101 - v100, v100);
+                    const float a11 = fmaf(wx, v111 - v110, v110);
+                    const float b0 = fmaf(wy, a01 - a00, a00);
+                    const float b1 = fmaf(wy, a11 - a10, a10);
+                    res = fmaf(wz, b1 - b0, b0);
+                    rare = CLEAN && (__float_as_uint(res) & 0x7f800000u) == 0x7f800000u;  // nan/inf tap
+                }
+                if (rare) {
+                    const EdgeCtx E = {P.iz, P.iy, P.ix, P.BZ, P.BY, P.BX, oz0, oy0, ox0, pitch, zs, P.cval, CLEAN};
+                    res = affine_edge_voxel(box, E, cz, cy, cx);
+                }
+                __stcs(row + 32 * i, res);
+            }
+        }
+    }
+}
+
+// Host: pick the output tile whose staged input box is smallest per output voxel.
+static bool choose_tile(AffineParams &P, int smem_limit, bool tma) {
+    static const int cand[][3] = {{8, 16, 64}, {4, 16, 64}, {4, 8, 64},  {2, 16, 64},  {8, 8, 64},   {4, 32, 64},
+                                  {2, 32, 64}, {1, 32, 64}, {4, 8, 128}, {2, 16, 128}, {2, 8, 128},  {1, 16, 128},
+                                  {4, 32, 32}, {2, 32, 32}, {8, 32, 32}, {1, 64, 64},  {1, 32, 128}, {2, 64, 32},
+                                  {8, 8, 128}, {4, 16, 128}, {8, 16, 128}, {4, 4, 128}, {8, 4, 128}};
+    double best = 1e300;
+    bool found = false;
+    int forced[3] = {0, 0, 0};
+    if (const char *f = getenv("SHRIMPY_AFFINE_TILE")) sscanf(f, "%d,%d,%d", &forced[0], &forced[1], &forced[2]);
+    for (const auto &c : cand) {
+        if (forced[0] && (c[0] != forced[0] || c[1] != forced[1] || c[2] != forced[2])) continue;
+        const int T[3] = {c[0], c[1], c[2]};  // not clipped to the output: TY must stay a power of two
+        long long B[3];
+        for (int a = 0; a < 3; ++a) {
+            double span = 0;
+            for (int b = 0; b < 3; ++b) span += std::fabs(P.M[4 * a + b]) * (T[b] - 1);
+            B[a] = (long long)std::ceil(span) + 3;
+        }
+        if (tma) B[2] = (B[2] + 3 + 3) / 4 * 4;           // TMA rows start and end on 16-byte boundaries
+        const long long pitch = tma ? B[2] : (B[2] | 1);  // cp.async rows sit at an odd pitch
+        const long long bytes = B[0] * B[1] * pitch * 4 + 128;
+        if (bytes > smem_limit || B[0] > 4096 || B[1] > 4096 || B[2] > 8192) continue;
+        if (tma && (B[0] > 256 || B[1] > 256 || B[2] > 256)) continue;
+        const double outputs = (double)T[0] * T[1] * T[2];
+        // cost: staged elements per output, short rows are penalised (poor coalescing), and a
+        // mild preference for larger tiles (fewer CTAs, per-row float64 set-up amortised)
+        double cost = (double)(B[0] * B[1] * B[2]) / outputs;
+        if (B[2] < 32) cost *= 32.0 / (double)B[2];
+        cost += 256.0 / outputs + (T[2] == 32 ? 0.15 : 0.0);
+        if (cost < best) {
+            best = cost;
+            found = true;
+            P.TZ = T[0]; P.TY = T[1]; P.TX = T[2];
+            P.log2TY = 0;
+            while ((1 << P.log2TY) < P.TY) ++P.log2TY;
+            P.BZ = (int)B[0]; P.BY = (int)B[1]; P.BX = (int)B[2];
+            P.pitch = (int)pitch;
+        }
+    }
+    return found;
 }
 
 }  // namespace shrimpy
@@ -108,11 +355,65 @@ extern "C" int shrimpy_affine_device(const float *d_in, float *d_out, int iz, in
     for (int i = 0; i < 12; ++i) P.M[i] = M[i];
     P.cval = cval;
     P.nan_to_zero = nan_to_zero;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+
+    const char *force = getenv("SHRIMPY_AFFINE_KERNEL");
+    bool want_gather = force && force[0] == 'g';
+    // the tiled kernel's fast coordinate split needs |c| < 2^28 everywhere on the output grid
+    for (int a = 0; a < 3; ++a) {
+        const double reach = std::fabs(M[4 * a + 3]) + std::fabs(M[4 * a]) * oz + std::fabs(M[4 * a + 1]) * oy +
+                             std::fabs(M[4 * a + 2]) * ox;
+        if (!(reach < 134217728.0)) want_gather = true;
+    }
+    const int smem_limit = 56 * 1024;  // 4 CTAs per SM: staging of one tile overlaps the maths of others
+    // TMA staging (dense pitch) when a warp's 32 consecutive o2 touch only a few input rows and the
+    // tensor map constraints hold; otherwise cp.async rows at an odd pitch.
+    bool tma = !(force && force[0] == 'c') && std::fabs(M[6]) * 32 <= 4.0 && std::fabs(M[2]) * 32 <= 4.0 &&
+               (reinterpret_cast<uintptr_t>(d_in) & 15u) == 0 && ix % 4 == 0 && tensor_map_encoder() != nullptr;
+    if (!want_gather && (choose_tile(P, smem_limit, tma) || (tma && !(tma = false) && choose_tile(P, smem_limit, false)))) {
+        P.tiles_x = (ox + P.TX - 1) / P.TX;
+        P.tiles_y = (oy + P.TY - 1) / P.TY;
+        P.tiles_z = (oz + P.TZ - 1) / P.TZ;
+        CUtensorMap tmap{};
+        if (tma) {
+            const cuuint64_t gdim[3] = {(cuuint64_t)ix, (cuuint64_t)iy, (cuuint64_t)iz};
+            const cuuint64_t gstride[2] = {(cuuint64_t)ix * 4, (cuuint64_t)ix * iy * 4};
+            const cuuint32_t bdim[3] = {(cuuint32_t)P.BX, (cuuint32_t)P.BY, (cuuint32_t)P.BZ};
+            P.tma_bytes = bdim[0] * bdim[1] * bdim[2] * 4u;
+            const cuuint32_t estr[3] = {1u, 1u, 1u};
+            const CUresult rc = tensor_map_encoder()(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(d_in),
+                                                     gdim, gstride, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (rc != CUDA_SUCCESS) return fail(SHRIMPY_ECUDA, "affine: cuTensorMapEncodeTiled failed (%d)", (int)rc);
+        }
+        if (P.tiles_y <= 65535 && (long long)P.tiles_x * P.tiles_z <= 2147483647LL) {
+            const size_t smem = (size_t)P.BZ * P.BY * P.pitch * sizeof(float) + 128;
+            void (*kern)(const CUtensorMap, const AffineParams) = nullptr;
+            const int items = P.TX / 32;
+#define SHRIMPY_PICK(I, C, T) affine_tile_kernel<I, C, T>
+#define SHRIMPY_PICK_I(C, T) (items == 1 ? SHRIMPY_PICK(1, C, T) : items == 2 ? SHRIMPY_PICK(2, C, T) : SHRIMPY_PICK(4, C, T))
+            if (nan_to_zero) kern = tma ? SHRIMPY_PICK_I(true, true) : SHRIMPY_PICK_I(true, false);
+            else kern = tma ? SHRIMPY_PICK_I(false, true) : SHRIMPY_PICK_I(false, false);
+#undef SHRIMPY_PICK_I
+#undef SHRIMPY_PICK
+            if (getenv("SHRIMPY_DEBUG"))
+                fprintf(stderr, "[shrimpy] affine tile T=(%d,%d,%d) B=(%d,%d,%d) pitch=%d tma=%d clean=%d smem=%zu grid=(%d,%d)\n",
+                        P.TZ, P.TY, P.TX, P.BZ, P.BY, P.BX, P.pitch, (int)tma, nan_to_zero, smem,
+                        P.tiles_x * P.tiles_z, P.tiles_y);
+            if (smem + 1024 > 48 * 1024)  // static smem and the per-CTA reserve count against the 48 KB default
+                SHRIMPY_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            kern<<<dim3((unsigned)(P.tiles_x * P.tiles_z), (unsigned)P.tiles_y), kTileThreads, smem, s>>>(tmap, P);
+            count_launch();
+            SHRIMPY_CUDA_TRY(cudaGetLastError());
+            return SHRIMPY_OK;
+        }
+    }
     const int per_block = kAffThreads * kAffItems;
     P.tiles_x = (ox + per_block - 1) / per_block;
     const long long gx = (long long)P.tiles_x * oy;
     if (gx > 2147483647LL || oz > 65535) return fail(SHRIMPY_EINVAL, "affine: output too large for the grid");
-    affine_gather_kernel<<<dim3((unsigned)gx, (unsigned)oz), kAffThreads, 0, static_cast<cudaStream_t>(stream)>>>(P);
+    affine_gather_kernel<<<dim3((unsigned)gx, (unsigned)oz), kAffThreads, 0, s>>>(P);
     count_launch();
     SHRIMPY_CUDA_TRY(cudaGetLastError());
     return SHRIMPY_OK;

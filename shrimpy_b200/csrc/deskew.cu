@@ -43,6 +43,7 @@ struct DeskewParams {
     int nz_cap;    // scan slices per staged row (multiple of 8, <= 256)
     int tiles_x;   // number of raw-x tiles
     int tiles_o2;  // number of o2 tiles
+    int order;     // 0: raw-x tile fastest in blockIdx.x, 1: o2 tile fastest
 };
 
 // Arithmetic shared by every kernel in this file (so that they agree bit for bit):
@@ -176,6 +177,12 @@ struct Chunk<float> {
     }
 };
 
+#ifndef SHRIMPY_STORE_PLAIN
+#define SHRIMPY_STORE(p, v) __stcs((p), (v))   // streaming (evict-first): outputs are never re-read
+#else
+#define SHRIMPY_STORE(p, v) (*(p) = (v))
+#endif
+
 constexpr int kTmaThreads = 256;
 constexpr int kRowBytes = 128;  // one staged row = 128 B of raw x = one swizzle span
 constexpr int kMaxTmaAvg = 4;   // template instantiations exist for n = 1..4
@@ -194,8 +201,8 @@ __global__ void __launch_bounds__(kTmaThreads, 3)
     const uint8_t *tile = smem_dyn + pad;
     const uint32_t region_bytes = (uint32_t)P.nz_cap * kRowBytes;
 
-    const int tx = blockIdx.x % P.tiles_x;
-    const int t2 = blockIdx.x / P.tiles_x;
+    const int tx = P.order ? blockIdx.x / P.tiles_o2 : blockIdx.x % P.tiles_x;
+    const int t2 = P.order ? blockIdx.x % P.tiles_o2 : blockIdx.x / P.tiles_x;
     const int p = P.p0 + blockIdx.y;
     const int x0 = tx * TX;
     const int c0 = P.cbeg + t2 * P.T2;
@@ -318,7 +325,7 @@ __global__ void __launch_bounds__(kTmaThreads, 3)
             if (xvalid >= EPC) {
 #pragma unroll
                 for (int j = 0; j < EPC; ++j) {
-                    __stcs(reinterpret_cast<float *>(ptr), r[j]);
+                    SHRIMPY_STORE(reinterpret_cast<float *>(ptr), r[j]);
                     ptr -= row_bytes;
                     asm volatile("" : "+l"(ptr));  // keep a stepped pointer (2 adds), not base+offset (4)
                 }
@@ -357,7 +364,7 @@ static int launch_direct(const DeskewParams &Pin, cudaStream_t stream) {
 template <typename T, int NAVG>
 static int launch_tma_n(const CUtensorMap &tmap, const DeskewParams &P, size_t smem, cudaStream_t stream) {
     auto kern = deskew_tma_kernel<T, NAVG>;
-    if (smem > 48 * 1024)
+    if (smem + 1024 > 48 * 1024)  // static smem counts against the 48 KB default as well
         SHRIMPY_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<dim3((unsigned)((long long)P.tiles_x * P.tiles_o2), (unsigned)P.pcount), kTmaThreads, smem, stream>>>(tmap, P);
     count_launch();
@@ -407,6 +414,7 @@ static int launch_tma(const DeskewParams &Pin, cudaStream_t stream, bool *used, 
     }
     P.tiles_x = (P.X + TX - 1) / TX;
     P.tiles_o2 = (P.cend - P.cbeg + P.T2 - 1) / P.T2;
+    P.order = env_int("SHRIMPY_DESKEW_ORDER", 0) ? 1 : 0;
     if ((long long)P.tiles_x * P.tiles_o2 > 2147483647LL) {
         if (required) return fail(SHRIMPY_EINVAL, "deskew: grid too large");
         return SHRIMPY_OK;

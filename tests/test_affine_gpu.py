@@ -37,7 +37,17 @@ def _run(env, vol, M, shape, **kw):
     return out.cpu().numpy()
 
 
-def test_golden_vectors(env):
+@pytest.fixture(params=["tile", "gather"])
+def kernel_choice(request, monkeypatch):
+    """Run a test through the shared-memory tiled kernel and through the plain gather kernel."""
+    if request.param == "gather":
+        monkeypatch.setenv("SHRIMPY_AFFINE_KERNEL", "gather")
+    else:
+        monkeypatch.delenv("SHRIMPY_AFFINE_KERNEL", raising=False)
+    return request.param
+
+
+def test_golden_vectors(env, kernel_choice):
     data = np.load(GOLDEN / "deskew_small.npz")
     vol = data["affine_general__vol"]
     for tag in ("general", "rot90"):
@@ -50,7 +60,7 @@ def test_golden_vectors(env):
 
 @pytest.mark.parametrize("shape_in,shape_out", [((20, 64, 80), (20, 64, 80)), ((11, 33, 47), (13, 50, 129)),
                                                   ((1, 5, 7), (1, 5, 7)), ((6, 40, 40), (0, 3, 3))])
-def test_general_matrix_matches_scipy(env, shape_in, shape_out):
+def test_general_matrix_matches_scipy(env, shape_in, shape_out, kernel_choice):
     _, _, o, _ = env
     rng = np.random.default_rng(sum(shape_in))
     vol = rng.standard_normal(shape_in).astype(np.float32)
@@ -77,7 +87,7 @@ def test_identity_and_integer_shift_are_exact(env):
     assert np.array_equal(got, want)
 
 
-def test_rot90_scale_onto_deskewed_grid(env):
+def test_rot90_scale_onto_deskewed_grid(env, kernel_choice):
     """Mantis-like label-free -> fluorescence registration: in-plane 90 deg rotation x 1.288 + shift."""
     _, _, o, c = env
     rng = np.random.default_rng(6)
@@ -89,7 +99,7 @@ def test_rot90_scale_onto_deskewed_grid(env):
     assert np.array_equal(got == 0.0, want == 0.0)
 
 
-def test_nan_to_num_and_numpy_front_end(env):
+def test_nan_to_num_and_numpy_front_end(env, kernel_choice):
     torch, register, o, _ = env
     rng = np.random.default_rng(7)
     vol = rng.standard_normal((5, 20, 24)).astype(np.float32)
@@ -104,6 +114,21 @@ def test_nan_to_num_and_numpy_front_end(env):
     assert np.max(np.abs(got[far] - want[far])) <= 1e-5
     with pytest.raises(ValueError):
         register.apply_affine_transform(vol, np.ones((4, 4)), vol.shape)
+
+
+def test_tile_and_gather_kernels_agree(env, monkeypatch):
+    rng = np.random.default_rng(11)
+    vol = rng.standard_normal((16, 150, 170)).astype(np.float32)
+    for M in (np.array([[1.0, 0, 0, 0.5], [0, 0, -1.288, 160.0], [0, 1.288, 0, -3.0], [0, 0, 0, 1]]),
+              np.array([[0.9, 0.05, 0.02, 0.3], [0.01, 1.1, -0.07, 2.0], [0.03, 0.06, 0.95, -1.5], [0, 0, 0, 1]]),
+              np.diag([2.5, 0.4, 3.0, 1.0])):
+        monkeypatch.delenv("SHRIMPY_AFFINE_KERNEL", raising=False)
+        a = _run(env, vol, M, (14, 120, 200), cval=1.5)
+        monkeypatch.setenv("SHRIMPY_AFFINE_KERNEL", "gather")
+        b = _run(env, vol, M, (14, 120, 200), cval=1.5)
+        # same geometry bit for bit; the tiled kernel truncates the lerp weights to 23 bits
+        assert np.array_equal(a == 1.5, b == 1.5)
+        assert_close_range(a, b, AFFINE_TOL, "tile vs gather")
 
 
 def test_medium_volume_vs_c_oracle(env):

@@ -55,6 +55,7 @@ if __name__ == "__main__":
     ap.add_argument("--cases", default="cfg2")
     args = ap.parse_args()
     print("peak", PEAK, torch.cuda.get_device_name(0))
+    args.cases = args.cases.split(",")
     if "cfg2" in args.cases:
         for dtype in ("u16", "f32"):
             for kernel in ("tma", "direct"):
@@ -71,3 +72,71 @@ if __name__ == "__main__":
     if "cfg1" in args.cases:
         for keep in (False, True):
             print(json.dumps(time_deskew((101, 256, 256), "u16", 1, keep, "tma", reps=50)), flush=True)
+    if "sweep" in args.cases:
+        for n, keep in ((1, False), (1, True), (3, False)):
+            for t2 in (64, 128, 256):
+                os.environ["SHRIMPY_DESKEW_T2"] = str(t2)
+                print("T2", t2, json.dumps(time_deskew((600, 300, 2048), "u16", n, keep, "tma", nbuf=1 if (keep and n == 1) else 2)), flush=True)
+        os.environ.pop("SHRIMPY_DESKEW_T2")
+    if "affine" in args.cases:
+        from shrimpy_b200 import register
+
+        def rot(a, b, c):
+            a, b, c = np.deg2rad([a, b, c])
+            Rz = np.array([[1, 0, 0], [0, np.cos(a), -np.sin(a)], [0, np.sin(a), np.cos(a)]])
+            Ry = np.array([[np.cos(b), 0, np.sin(b)], [0, 1, 0], [-np.sin(b), 0, np.cos(b)]])
+            Rx = np.array([[np.cos(c), -np.sin(c), 0], [np.sin(c), np.cos(c), 0], [0, 0, 1]])
+            return Rz @ Ry @ Rx
+
+        shape = (107, 2048, 2048)
+        vol = torch.randn(shape, device="cuda")
+        Mg = np.eye(4)
+        Mg[:3, :3] = rot(2.0, 1.0, 3.0) @ np.diag([1.03, 0.97, 1.1])
+        Mg[:3, 3] = [0.4, -1.2, 2.3]
+        M90 = np.array([[1.0, 0, 0, 3.5], [0, 0, -1.288, 2040.0], [0, 1.288, 0, -20.0], [0, 0, 0, 1]])
+        Mi = np.eye(4)
+        for name, M, oshape in (("identity", Mi, shape), ("general", Mg, shape), ("rot90", M90, (100, 2048, 1279))):
+            out = torch.empty(oshape, device="cuda")
+            if os.environ.get("DEVBENCH_ONCE"):
+                register.affine_transform_zyx(vol, M, oshape, out=out)
+                torch.cuda.synchronize()
+                continue
+            for _ in range(3):
+                register.affine_transform_zyx(vol, M, oshape, out=out)
+            torch.cuda.synchronize()
+            ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(8)]
+            for a, b in ev:
+                a.record()
+                register.affine_transform_zyx(vol, M, oshape, out=out)
+                b.record()
+            torch.cuda.synchronize()
+            ms = float(np.median([a.elapsed_time(b) for a, b in ev]))
+            inside = float((out != 0).float().mean())
+            nbytes = vol.numel() * 4 + out.numel() * 4
+            print(json.dumps(dict(case=name, out=oshape, ms=round(ms, 4), gbs_alg=round(nbytes / ms / 1e6, 1),
+                                  frac=round(nbytes / ms / 1e6 / PEAK, 3), gvox_out=round(out.numel() / ms / 1e6, 1),
+                                  inside=round(inside, 3))), flush=True)
+    if "afftile" in args.cases:
+        from shrimpy_b200 import register
+        shape = (107, 2048, 2048)
+        vol = torch.randn(shape, device="cuda")
+        out = torch.empty(shape, device="cuda")
+        Mi = np.eye(4); Mi[:3, 3] = [0.3, 0.4, 0.5]
+        for mode in ("tma", "cpasync"):
+            if mode == "cpasync":
+                os.environ["SHRIMPY_AFFINE_KERNEL"] = "cpasync"
+            for tile in ("8,16,64", "4,16,64", "4,8,64", "8,8,64", "4,8,128", "2,16,128", "8,8,128", "4,16,128", "4,32,32", "8,32,32"):
+                os.environ["SHRIMPY_AFFINE_TILE"] = tile
+                try:
+                    for _ in range(2):
+                        register.affine_transform_zyx(vol, Mi, shape, out=out)
+                    torch.cuda.synchronize()
+                    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    a.record()
+                    for _ in range(5):
+                        register.affine_transform_zyx(vol, Mi, shape, out=out)
+                    b.record(); torch.cuda.synchronize()
+                    print(mode, tile, round(a.elapsed_time(b) / 5, 3), "ms", flush=True)
+                except Exception as e:
+                    print(mode, tile, "failed", str(e)[:80])
+        os.environ.pop("SHRIMPY_AFFINE_TILE"); os.environ.pop("SHRIMPY_AFFINE_KERNEL", None)
