@@ -40,10 +40,20 @@ class ScanShard:
     """What one rank owns, computes and needs in a scan-axis split."""
 
     rank: int
-    own_z: Tuple[int, int]        # raw scan slices this rank holds before the exchange  [z0, z1)
-    cols: Tuple[int, int]         # output columns (o2) this rank computes               [c0, c1)
-    need_z: Tuple[int, int]       # raw scan slices its columns read                      [z0, z1)
-    interior_cols: Tuple[int, int]  # sub-range of cols whose taps lie inside own_z       [c0, c1) (may be empty)
+    own_z: Tuple[int, int]          # raw scan slices this rank holds before the exchange  [z0, z1)
+    cols: Tuple[int, int]           # output columns (o2) this rank computes               [c0, c1)
+    need_z: Tuple[int, int]         # raw scan slices its columns read                      [z0, z1)
+    interior_cols: Tuple[int, int]  # sub-range of cols whose taps lie inside own_z         [c0, c1) (may be empty)
+    low_need_z: Tuple[int, int]     # slices read by the columns below the interior run  (cols[0] .. interior[0])
+    high_need_z: Tuple[int, int]    # slices read by the columns above the interior run  (interior[1] .. cols[1])
+
+    @property
+    def low_cols(self) -> Tuple[int, int]:
+        return (self.cols[0], self.interior_cols[0])
+
+    @property
+    def high_cols(self) -> Tuple[int, int]:
+        return (self.interior_cols[1], self.cols[1])
 
     @property
     def halo_below(self) -> Tuple[int, int]:
@@ -54,12 +64,19 @@ class ScanShard:
         return (min(self.need_z[1], max(self.own_z[1], self.need_z[0])), self.need_z[1])
 
 
+def _needs(g: DeskewGeometry, c0: int, c1: int) -> Tuple[int, int]:
+    if c1 <= c0:
+        return (0, 0)
+    _, need = window_needs(g, 0, g.out_shape[0], c0, c1 - c0)
+    return (int(need[0]), int(need[1])) if need[1] > need[0] else (0, 0)
+
+
 def plan_scan_split(g: DeskewGeometry, world_size: int, align: int = 32) -> List[ScanShard]:
     """Cut the output columns into ``world_size`` contiguous ranges (multiples of ``align`` columns) and
     derive the raw slices each range reads.  Raw ownership boundaries follow the column boundaries
     (the scan index of a range's first column at tilt row 0), so the halo is almost entirely below."""
     Z, Y, _ = g.raw_shape
-    Yn, _, Xp = g.out_shape
+    Xp = g.out_shape[2]
     if world_size < 1:
         raise ValueError("world_size must be positive")
     edges = [min(Xp, int(round(Xp * i / world_size / align)) * align) for i in range(world_size)] + [Xp]
@@ -75,13 +92,10 @@ def plan_scan_split(g: DeskewGeometry, world_size: int, align: int = 32) -> List
     for i in range(world_size):
         c0, c1 = edges[i], edges[i + 1]
         own = (own_edges[i], own_edges[i + 1])
-        if c1 > c0:
-            _, need = window_needs(g, 0, Yn, c0, c1 - c0)
-        else:
+        need = _needs(g, c0, c1)
+        if need == (0, 0):
             need = (own[0], own[0])
-        if need[1] <= need[0]:
-            need = (own[0], own[0])
-        # widest run of columns, starting anywhere in [c0, c1), that needs nothing outside own_z
+        # the run of columns that needs nothing outside own_z (columns are monotone in z: one run)
         lo, hi = c0, c0
         if c1 > c0 and own[1] > own[0]:
             cols = np.arange(c0, c1)
@@ -92,49 +106,53 @@ def plan_scan_split(g: DeskewGeometry, world_size: int, align: int = 32) -> List
             hi_need = np.minimum(np.floor(np.clip(zmax, 0, Z - 1)) + 1, Z - 1)
             ok = (~inside_vol) | ((lo_need >= own[0]) & (hi_need < own[1]))
             if ok.any():
-                # columns are monotone in z, so the admissible set is one run
                 first = int(np.argmax(ok))
                 last = first
                 while last + 1 < ok.size and ok[last + 1]:
                     last += 1
                 lo, hi = c0 + first, c0 + last + 1
-        shards.append(ScanShard(i, own, (c0, c1), (int(need[0]), int(need[1])), (lo, hi)))
+        shards.append(ScanShard(i, own, (c0, c1), need, (lo, hi), _needs(g, c0, lo), _needs(g, hi, c1)))
     return shards
 
 
 def exchange_halos(own_slab, shards: Sequence[ScanShard], rank: int, *, group=None):
-    """Assemble this rank's needed slab ``raw[need_z[0]:need_z[1]]`` from its own slices and its peers'.
+    """Start the neighbour exchange for this rank's two boundary column ranges.
 
-    ``own_slab`` is a torch tensor ``(own_z1-own_z0, Y, X)`` (CPU with gloo, CUDA with NCCL).  Every
-    rank posts the sends its peers need and the receives it needs (``batch_isend_irecv``), so the
-    pattern is a sparse neighbour exchange, not a collective.  Returns ``(slab, requests)`` -- the
-    caller may compute interior columns from ``own_slab`` before waiting on ``requests``.
+    ``own_slab`` is a torch tensor ``(own_z1-own_z0, Y, X)`` (CPU with gloo, CUDA with NCCL).  For the
+    columns below and above the interior run, a small slab ``raw[z0:z1]`` is assembled from this rank's
+    own slices (copied) and its peers' (received).  Every rank posts the sends its peers need and the
+    receives it needs in one ``batch_isend_irecv`` -- a sparse neighbour exchange, not a collective;
+    both sides enumerate (peer, low, high) in the same order so the pairs match.
+    Returns ``((low_slab, low_z0), (high_slab, high_z0), requests)``.
     """
     import torch
     import torch.distributed as dist
 
+    def wire(t):   # torch's NCCL backend has no 16-bit integer types: ship the same bytes as uint8
+        return t.view(torch.uint8) if t.dtype in (torch.uint16, torch.int16) else t
+
     me = shards[rank]
-    z0, z1 = me.need_z
-    slab = torch.empty((max(z1 - z0, 0),) + tuple(own_slab.shape[1:]), dtype=own_slab.dtype, device=own_slab.device)
-    # own part
-    a, b = max(z0, me.own_z[0]), min(z1, me.own_z[1])
-    if b > a:
-        slab[a - z0:b - z0].copy_(own_slab[a - me.own_z[0]:b - me.own_z[0]])
-    ops = []
+    ops, slabs = [], []
+    for z0, z1 in (me.low_need_z, me.high_need_z):
+        slab = torch.empty((max(z1 - z0, 0),) + tuple(own_slab.shape[1:]), dtype=own_slab.dtype, device=own_slab.device)
+        a, b = max(z0, me.own_z[0]), min(z1, me.own_z[1])
+        if b > a:
+            slab[a - z0:b - z0].copy_(own_slab[a - me.own_z[0]:b - me.own_z[0]])
+        slabs.append((slab, z0))
     for other in shards:
         if other.rank == rank:
             continue
-        # what I need from `other`
-        a, b = max(z0, other.own_z[0]), min(z1, other.own_z[1])
-        if b > a:
-            ops.append(dist.P2POp(dist.irecv, slab[a - z0:b - z0], other.rank, group=group))
-        # what `other` needs from me
-        a, b = max(other.need_z[0], me.own_z[0]), min(other.need_z[1], me.own_z[1])
-        if b > a:
-            ops.append(dist.P2POp(dist.isend, own_slab[a - me.own_z[0]:b - me.own_z[0]].contiguous(), other.rank,
-                                  group=group))
+        for which, (z0, z1) in enumerate((me.low_need_z, me.high_need_z)):      # what I need from `other`
+            a, b = max(z0, other.own_z[0]), min(z1, other.own_z[1])
+            if b > a:
+                ops.append(dist.P2POp(dist.irecv, wire(slabs[which][0][a - z0:b - z0]), other.rank, group=group))
+        for z0, z1 in (other.low_need_z, other.high_need_z):                     # what `other` needs from me
+            a, b = max(z0, me.own_z[0]), min(z1, me.own_z[1])
+            if b > a:
+                ops.append(dist.P2POp(dist.isend, wire(own_slab[a - me.own_z[0]:b - me.own_z[0]]), other.rank,
+                                      group=group))
     reqs = dist.batch_isend_irecv(ops) if ops else []
-    return slab, reqs
+    return slabs[0], slabs[1], reqs
 
 
 def deskew_scan_split(own_slab, g: DeskewGeometry, shards: Sequence[ScanShard], rank: int, *, cval: float = 0.0,
@@ -142,37 +160,40 @@ def deskew_scan_split(own_slab, g: DeskewGeometry, shards: Sequence[ScanShard], 
     """Deskew this rank's output columns of one volume that is split along the scan axis.
 
     Returns the compact tensor ``out[:, :, c0:c1]``.  ``window_fn(slab, g, p_begin, p_count, c_begin,
-    c_count, y_origin, z_origin, cval)`` defaults to the CUDA window kernel; the CPU tests inject a
-    stand-in.  Interior columns are computed from the rank's own slices while the halo travels.
+    c_count, y_origin, z_origin, cval)`` defaults to the CUDA window kernel (which writes straight into
+    the strided output view); the CPU tests inject a stand-in.  The interior columns are computed from
+    the rank's own slices while the halo for the boundary columns is in flight.
     """
     import torch
 
-    if window_fn is None:
+    in_place = window_fn is None
+    if in_place:
         from .deskew import deskew_window
 
-        def window_fn(slab, g, p_begin, p_count, c_begin, c_count, y_origin, z_origin, cval):
+        def window_fn(slab, g, p_begin, p_count, c_begin, c_count, y_origin, z_origin, cval, out=None):
             return deskew_window(slab, g, p_begin=p_begin, p_count=p_count, c_begin=c_begin, c_count=c_count,
-                                 y_origin=y_origin, z_origin=z_origin, cval=cval)
+                                 y_origin=y_origin, z_origin=z_origin, cval=cval, out=out)
 
     me = shards[rank]
     Yn, X, _ = g.out_shape
     c0, c1 = me.cols
     out = torch.empty((Yn, X, c1 - c0), dtype=torch.float32, device=own_slab.device)
-    slab, reqs = exchange_halos(own_slab, shards, rank, group=group)
-    if slab.shape[0] == 0 and own_slab.shape[0] == 0:   # nothing of the volume maps into these columns
-        for r in reqs:
-            r.wait()
-        return out.fill_(cval)
-    i0, i1 = me.interior_cols
-    if i1 > i0:      # overlaps with the exchange
-        out[:, :, i0 - c0:i1 - c0] = window_fn(own_slab, g, 0, Yn, i0, i1 - i0, 0, me.own_z[0], cval)
+
+    def run(slab, z_origin, a, b):
+        if b <= a:
+            return
+        view = out[:, :, a - c0:b - c0]
+        if slab.shape[0] == 0:              # these columns read nothing from the volume
+            view.fill_(cval)
+        elif in_place:
+            window_fn(slab, g, 0, Yn, a, b - a, 0, z_origin, cval, out=view)
+        else:
+            view.copy_(window_fn(slab, g, 0, Yn, a, b - a, 0, z_origin, cval))
+
+    (low, low_z0), (high, high_z0), reqs = exchange_halos(own_slab, shards, rank, group=group)
+    run(own_slab, me.own_z[0], *me.interior_cols)     # overlaps with the exchange
     for r in reqs:
         r.wait()
-    for a, b in ((c0, i0 if i1 > i0 else c1), (i1, c1) if i1 > i0 else (c1, c1)):
-        if b > a:
-            z_origin = me.need_z[0]
-            src = slab if slab.shape[0] else own_slab
-            if slab.shape[0] == 0:
-                z_origin = me.own_z[0]
-            out[:, :, a - c0:b - c0] = window_fn(src, g, 0, Yn, a, b - a, 0, z_origin, cval)
+    run(low, low_z0, *me.low_cols)
+    run(high, high_z0, *me.high_cols)
     return out

@@ -1,0 +1,95 @@
+"""BASELINE configs[4]: one oversized volume (4000, 300, 2048) uint16, keep_overhang=True, n=1, split along
+the scan axis over the ranks of one box with an NVLink halo exchange (torchrun, one process per GPU).
+
+Every rank regenerates ALL raw slabs from per-slab seeds (so that it can also compute the single-GPU
+answer for its own columns and compare bit for bit), but the timed path only touches its own slab plus
+the halo it receives.  Prints one JSON line on rank 0.
+"""
+
+import argparse
+import json
+import os
+import sys
+from pathlib import Path
+
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+
+import torch
+import torch.distributed as dist
+
+import shrimpy_b200 as sb
+from shrimpy_b200 import sharding
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--shape", default="4000,300,2048")
+    ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--check", type=int, default=1)
+    args = ap.parse_args()
+    shape = tuple(int(v) for v in args.shape.split(","))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("MASTER_PORT", "29533")
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
+
+    g = sb.deskew_geometry(shape, 30.0, 0.39, True, 1)
+    shards = sharding.plan_scan_split(g, world)
+    me = shards[rank]
+
+    def slab_of(r):
+        z0, z1 = shards[r].own_z
+        gen = torch.Generator(device="cuda").manual_seed(1000 + r)
+        return torch.randint(100, 60000, (z1 - z0,) + shape[1:], dtype=torch.int32, device="cuda",
+                             generator=gen).to(torch.uint16)
+
+    own = slab_of(rank)
+    # warm-up (also builds NCCL channels)
+    piece = sharding.deskew_scan_split(own, g, shards, rank)
+    torch.cuda.synchronize()
+    dist.barrier()
+    times = []
+    for _ in range(args.reps):
+        dist.barrier()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        piece = sharding.deskew_scan_split(own, g, shards, rank)
+        b.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        times.append(float(t.item()))
+    ok = True
+    if args.check:
+        del own
+        full = torch.cat([slab_of(r) for r in range(world)], dim=0)
+        ref = sb.deskew_zyx(full, 30.0, 0.39, True, 1)
+        ok = bool(torch.equal(ref[:, :, me.cols[0]:me.cols[1]], piece))
+        flag = torch.tensor([int(ok)], device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        ok = bool(flag.item())
+        if rank == 0 and world == 1:
+            pass
+    halo = (me.halo_below[1] - me.halo_below[0] + me.halo_above[1] - me.halo_above[0]) * shape[1] * shape[2] * 2
+    halos = torch.tensor([halo], dtype=torch.float64, device="cuda")
+    dist.all_reduce(halos, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        ms = sorted(times)[len(times) // 2]
+        vin, vout = g.algorithmic_bytes
+        print(json.dumps({"config": f"scan-axis split {shape} uint16 keep_overhang=True n=1", "n_gpus": world,
+                          "ms": round(ms, 3), "gvoxel_out_per_s": round(vout / ms / 1e6, 1),
+                          "alg_gbs_total": round((vin * 2 + vout * 4) / ms / 1e6, 1),
+                          "max_halo_mb_per_rank": round(float(halos.item()) / 1e6, 1),
+                          "matches_single_gpu_bitwise": ok, "out_shape": g.out_shape,
+                          "interior_cols_frac": round(sum(s.interior_cols[1] - s.interior_cols[0] for s in shards) / g.out_shape[2], 3)}),
+              flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
