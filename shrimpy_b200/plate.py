@@ -135,7 +135,7 @@ def deskew_plate(src: Sequence[Position], settings, dst: Optional[Sequence[Posit
             free[slot].acquire()
             i, t, c = mine[k]
             t0 = time.perf_counter()
-            nbytes = src[i].array.read_stack_into(t, c, h_in[slot].numpy())
+            nbytes = src[i].array.read_stack_into(t, c, h_in[slot].numpy(), pool=io_pool)
             with lock:
                 stats.disk_read_bytes += nbytes
                 stats.load_seconds += time.perf_counter() - t0
@@ -146,7 +146,7 @@ def deskew_plate(src: Sequence[Position], settings, dst: Optional[Sequence[Posit
             i, t, c = mine[k]
             result = h_out[slot].numpy()
             t0 = time.perf_counter()
-            written = dst[i].array.write_stack(t, c, result) if dst is not None else 0
+            written = dst[i].array.write_stack(t, c, result, pool=io_pool) if dst is not None else 0
             if on_result is not None:
                 on_result(src[i].name, t, c, result)
             with lock:
@@ -156,8 +156,9 @@ def deskew_plate(src: Sequence[Position], settings, dst: Optional[Sequence[Posit
             free[slot].release()
 
         t_start = time.perf_counter()
-        # blocked loads (waiting for a slot) never exceed `depth`, so depth+1 workers cannot starve the writers
-        with ThreadPoolExecutor(max_workers=max(io_threads, depth + 1)) as pool:
+        # `pool` runs the per-unit stages (blocked loads never exceed `depth`, so 2*depth+1 workers cannot starve the
+        # writers); `io_pool` runs the byte-range pieces those stages fan out, and nothing in it ever blocks.
+        with ThreadPoolExecutor(max_workers=2 * depth + 1) as pool, ThreadPoolExecutor(max_workers=max(1, io_threads)) as io_pool:
             loads = {k: pool.submit(load, k) for k in range(min(depth, len(mine)))}
             tails = []
             for k in range(len(mine)):

@@ -27,10 +27,9 @@ import ctypes
 import ctypes.util
 import json
 import os
-import struct
 from dataclasses import dataclass, field
 from pathlib import Path
-from typing import Dict, Iterator, List, Optional, Sequence, Tuple
+from typing import List, Optional, Sequence, Tuple
 
 import numpy as np
 
@@ -261,30 +260,66 @@ class ZarrArray:
         Z, zc = self.shape[2], self.chunks[2]
         return [((t, c, k, 0, 0), slice(k * zc, min((k + 1) * zc, Z))) for k in range(-(-Z // zc))]
 
-    def read_stack_into(self, t: int, c: int, out: np.ndarray) -> int:
-        """Read the ``(Z, Y, X)`` stack of ``(t, c)`` into ``out``; z-chunks land in place. Returns disk bytes."""
+    def read_stack_into(self, t: int, c: int, out: np.ndarray, pool=None, piece_bytes: int = 32 << 20) -> int:
+        """Read the ``(Z, Y, X)`` stack of ``(t, c)`` into ``out``; z-chunks land in place. Returns disk bytes.
+
+        With ``pool`` (a ``ThreadPoolExecutor``) the work is cut into independent pieces -- byte ranges of
+        ``piece_bytes`` for uncompressed chunks (``os.preadv`` straight into the destination, the GIL is
+        released), whole chunks for compressed ones -- and read concurrently.  Only the part of a partial
+        last chunk that holds data is read.
+        """
         self._check_tczyx()
         Z, Y, X = self.shape[2:]
         if tuple(out.shape) != (Z, Y, X) or out.dtype != self.dtype or not out.flags.c_contiguous:
             raise ValueError(f"out must be a C-contiguous {self.dtype} array of shape {(Z, Y, X)}")
-        total, zc = 0, self.chunks[2]
-        scratch = None
+        zc = self.chunks[2]
+        tasks = []
         for index, zs in self.stack_chunks(t, c):
-            if zs.stop - zs.start == zc:
-                total += self.read_chunk_into(index, out[zs].reshape(self.chunks))
-            else:                                           # last, partial chunk is stored full-size
-                if scratch is None:
-                    scratch = np.empty(self.chunks, dtype=self.dtype)
-                total += self.read_chunk_into(index, scratch)
-                out[zs] = scratch[0, 0, :zs.stop - zs.start]
-        return total
+            nz = zs.stop - zs.start
+            path = self.chunk_path(index)
+            if not self.zstd and self.shard_inner is None:
+                if not path.exists():
+                    out[zs] = self.fill_value
+                    continue
+                view = memoryview(out[zs].reshape(-1).view(np.uint8))       # the data-bearing prefix of the chunk
+                for off in range(0, len(view), piece_bytes):
+                    tasks.append((_pread_piece, (path, off, view[off:off + piece_bytes])))
+            elif nz == zc:
+                tasks.append((self.read_chunk_into, (index, out[zs].reshape(self.chunks))))
+            else:                                           # compressed partial chunk: decode, then copy the prefix
+                tasks.append((self._read_partial, (index, out[zs])))
+        if pool is None or len(tasks) <= 1:
+            return sum(fn(*a) for fn, a in tasks)
+        return sum(f.result() for f in [pool.submit(fn, *a) for fn, a in tasks])
 
-    def write_stack(self, t: int, c: int, data: np.ndarray) -> int:
+    def _read_partial(self, index, dest: np.ndarray) -> int:
+        scratch = np.empty(self.chunks, dtype=self.dtype)
+        n = self.read_chunk_into(index, scratch)
+        dest[...] = scratch[0, 0, :dest.shape[0]]
+        return n
+
+    def write_stack(self, t: int, c: int, data: np.ndarray, pool=None) -> int:
+        """Write stack ``(t, c)``; with ``pool`` the chunk files are written concurrently (one writer per file:
+        concurrent writers of ONE file serialise on its inode lock, so parallelism comes from the chunk count)."""
         self._check_tczyx()
-        total = 0
-        for index, zs in self.stack_chunks(t, c):
-            total += self.write_chunk(index, data[zs][None, None])
-        return total
+        jobs = [(index, data[zs][None, None]) for index, zs in self.stack_chunks(t, c)]
+        if pool is None or len(jobs) <= 1:
+            return sum(self.write_chunk(index, block) for index, block in jobs)
+        return sum(f.result() for f in [pool.submit(self.write_chunk, index, block) for index, block in jobs])
+
+
+def _pread_piece(path, offset: int, dest: memoryview) -> int:
+    fd = os.open(path, os.O_RDONLY)
+    try:
+        done = 0
+        while done < len(dest):
+            n = os.preadv(fd, [dest[done:]], offset + done)
+            if n <= 0:
+                raise IOError(f"{path}: short read at {offset + done}")
+            done += n
+        return done
+    finally:
+        os.close(fd)
 
 
 # ---- OME-NGFF 0.5 HCS plate ----------------------------------------------------------------------

@@ -33,6 +33,7 @@ def main():
     ap.add_argument("--io-threads", type=int, default=6)
     ap.add_argument("--write", type=int, default=0, help="1: also write the deskewed plate back to the store")
     ap.add_argument("--zstd", type=int, default=-1)
+    ap.add_argument("--out-z-chunk", type=int, default=10)
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -58,7 +59,7 @@ def main():
     gen_s = time.perf_counter() - t0
     settings = DeskewSettings(ls_angle_deg=30.0, pixel_size_um=0.116, px_to_scan_ratio=0.39, keep_overhang=False,
                               average_n_slices=3)
-    dst = plate.create_deskewed_plate(root / "deskewed.zarr", src, settings) if args.write else None
+    dst = plate.create_deskewed_plate(root / "deskewed.zarr", src, settings, z_chunk=args.out_z_chunk) if args.write else None
     plate.deskew_plate(src[:1], settings, depth=1)                       # warm-up (pinned allocs, first launch)
     if world > 1:
         dist.barrier()
