@@ -133,31 +133,36 @@ __device__ __forceinline__ void cp_async4(uint32_t dst, const float *src) {
 
 // Slow, fully general voxel: exact edge rule (c == dim-1 is inside, the second tap folds onto the
 // first there) and clamped box indices.  Only voxels on the rim of the input volume come here.
-struct EdgeCtx {
-    int iz, iy, ix;     // input dims
-    int BZ, BY, BX;     // staged box dims
-    int oz0, oy0, ox0;  // box origin
-    int pitch, zs;
-    float cval;
-    int clean;          // apply nan_to_num to the taps
-};
-
-__device__ __noinline__ float affine_edge_voxel(const float *box, EdgeCtx E, double cz, double cy, double cx) {
+// Slow, fully general voxel, recomputed from the output index with scipy's exact coordinate
+// arithmetic: exact edge rule (c == dim-1 is inside, the second tap folds onto the first there),
+// clamped box indices, optional nan_to_num of the taps.  Voxels within one input voxel of the rim of
+// the input volume, voxels outside it and voxels with a non-finite fast-path result come here.
+__device__ __noinline__ float affine_edge_voxel(const float *box, const AffineParams *Pp, int o0, int o1, int o2,
+                                                int oz0, int oy0, int ox0, int clean_taps) {
+    const AffineParams &P = *Pp;
+    double c[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        double t = __dadd_rn(P.M[4 * a + 3], __dmul_rn((double)o0, P.M[4 * a + 0]));
+        t = __dadd_rn(t, __dmul_rn((double)o1, P.M[4 * a + 1]));
+        c[a] = __dadd_rn(t, __dmul_rn((double)o2, P.M[4 * a + 2]));
+    }
     int z0, y0, x0;
     float wz, wy, wx;
-    bool in = split_coord(cz, E.iz, z0, wz);
-    in &= split_coord(cy, E.iy, y0, wy);
-    in &= split_coord(cx, E.ix, x0, wx);
-    if (!in) return E.cval;
-    const int dz = (z0 + 1 < E.iz) ? E.zs : 0;
-    const int dy = (y0 + 1 < E.iy) ? E.pitch : 0;
-    const int dx = (x0 + 1 < E.ix) ? 1 : 0;
-    const int bz = min(max(z0 - E.oz0, 0), E.BZ - 1);
-    const int by = min(max(y0 - E.oy0, 0), E.BY - 1);
-    const int bx = min(max(x0 - E.ox0, 0), E.BX - 1);
-    const float *q = box + bz * E.zs + by * E.pitch + bx;
+    bool in = split_coord(c[0], P.iz, z0, wz);
+    in &= split_coord(c[1], P.iy, y0, wy);
+    in &= split_coord(c[2], P.ix, x0, wx);
+    if (!in) return P.cval;
+    const int zs = P.BY * P.pitch;
+    const int dz = (z0 + 1 < P.iz) ? zs : 0;
+    const int dy = (y0 + 1 < P.iy) ? P.pitch : 0;
+    const int dx = (x0 + 1 < P.ix) ? 1 : 0;
+    const int bz = min(max(z0 - oz0, 0), P.BZ - 1);
+    const int by = min(max(y0 - oy0, 0), P.BY - 1);
+    const int bx = min(max(x0 - ox0, 0), P.BX - 1);
+    const float *q = box + bz * zs + by * P.pitch + bx;
     float v[8] = {q[0], q[dx], q[dy], q[dy + dx], q[dz], q[dz + dx], q[dz + dy], q[dz + dy + dx]};
-    if (E.clean) {
+    if (clean_taps) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) v[i] = clean(v[i]);
     }
@@ -171,10 +176,12 @@ __device__ __noinline__ float affine_edge_voxel(const float *box, EdgeCtx E, dou
 }
 
 // ITEMS = TX / 32 output columns per lane and tile row; CLEAN = nan_to_num semantics;
-// USE_TMA = stage the box with one TMA load (dense pitch) instead of cp.async rows (odd pitch).
-template <int ITEMS, bool CLEAN, bool USE_TMA>
+// USE_TMA = stage the box with one TMA load (dense pitch) instead of cp.async rows (odd pitch);
+// ZSEP = the input (y, x) of a voxel do not depend on o0 (M[1][0] == M[2][0] == 0: in-plane
+// registration, z shift/scale) -> the bilinear value of an input plane is shared by consecutive o0.
+template <int ITEMS, bool CLEAN, bool USE_TMA, bool ZSEP>
 __global__ void __launch_bounds__(kTileThreads, 2)
-    affine_tile_kernel(const __grid_constant__ CUtensorMap tmap, const AffineParams P) {
+    affine_tile_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ AffineParams P) {
     extern __shared__ __align__(128) float box_raw[];
     __shared__ int s_org[3];
     __shared__ __align__(8) uint64_t bar;
@@ -239,37 +246,80 @@ __global__ void __launch_bounds__(kTileThreads, 2)
         __syncthreads();
     }
 
-    // Resample: warp w takes tile rows (lz,ly) = w, w+8, ...; lanes own consecutive o2.
-    const int tile_rows = P.TZ << P.log2TY;
+    // Resample, column-marching: a thread owns output columns (o1, o2) -- lanes hold consecutive o2, so
+    // stores are coalesced -- and walks o0 through the tile.  The coordinate advances by ONE float64 add
+    // per axis and voxel (c += M_a0).  That drifts from scipy's ((M_a3 + o0 M_a0) + o1 M_a1) + o2 M_a2 by
+    // < 1e-11 voxel, harmless for a voxel whose taps are at least one input voxel away from the rim (the
+    // interpolant is continuous); every other voxel is recomputed exactly by affine_edge_voxel.
     const int org_off = oz0 * zs + oy0 * pitch + ox0;
-    const unsigned hz = P.iz - 1, hy = P.iy - 1, hx = P.ix - 1;
-    const double m02 = P.M[2], m12 = P.M[6], m22 = P.M[10];
-    const int col = t0x + lane;
-    for (int r = warp; r < tile_rows; r += kTileThreads / 32) {
-        const int lz = r >> P.log2TY, ly = r & (P.TY - 1);
-        const int o0 = t0z + lz, o1 = t0y + ly;
-        if (o0 >= P.oz || o1 >= P.oy) continue;
-        double base[3];
-#pragma unroll
-        for (int a = 0; a < 3; ++a) {
-            const double t = __dadd_rn(P.M[4 * a + 3], __dmul_rn((double)o0, P.M[4 * a + 0]));
-            base[a] = __dadd_rn(t, __dmul_rn((double)o1, P.M[4 * a + 1]));
-        }
-        float *row = P.out + ((long long)o0 * P.oy + o1) * P.ox + col;
-#pragma unroll
+    const unsigned hz = (unsigned)max(P.iz - 3, 0), hy = (unsigned)max(P.iy - 3, 0), hx = (unsigned)max(P.ix - 3, 0);
+    const unsigned uz = (unsigned)P.iz, uy = (unsigned)P.iy, ux = (unsigned)P.ix;
+    const double sz = P.M[0], sy = P.M[4], sx = P.M[8];   // per-step increments along o0
+    const int nz = min(P.TZ, P.oz - t0z);
+    const long long plane = (long long)P.oy * P.ox;
+    for (int ly = warp; ly < P.TY; ly += kTileThreads / 32) {
+        const int o1 = t0y + ly;
+        if (o1 >= P.oy) break;
+#pragma unroll 1
         for (int i = 0; i < ITEMS; ++i) {
-            const int o2 = col + 32 * i;
-            if (o2 < P.ox) {
-                const double cz = __dadd_rn(base[0], __dmul_rn((double)o2, m02));
-                const double cy = __dadd_rn(base[1], __dmul_rn((double)o2, m12));
-                const double cx = __dadd_rn(base[2], __dmul_rn((double)o2, m22));
-                float wz, wy, wx;
-                const int z0 = split_fast(cz, wz), y0 = split_fast(cy, wy), x0 = split_fast(cx, wx);
-                float res = 0.f;
-                bool rare = true;  // rim of the input volume, outside, or a non-finite tap
-                if ((unsigned)z0 < hz && (unsigned)y0 < hy && (unsigned)x0 < hx) {
-                    // interior: 0 <= c < dim-1 on every axis, both taps exist, no clamping needed
-                    const float *q = box + (z0 * zs + y0 * pitch + x0 - org_off);
+            const int o2 = t0x + lane + 32 * i;
+            if (o2 >= P.ox) break;
+            double cz = ((P.M[3] + (double)t0z * sz) + (double)o1 * P.M[1]) + (double)o2 * P.M[2];
+            double cy = ((P.M[7] + (double)t0z * sy) + (double)o1 * P.M[5]) + (double)o2 * P.M[6];
+            double cx = ((P.M[11] + (double)t0z * sx) + (double)o1 * P.M[9]) + (double)o2 * P.M[10];
+            float *ptr0 = P.out + ((long long)t0z * P.oy + o1) * P.ox + o2;
+            float *ptr = ptr0;
+            // Steps that need the exact slow path (near the rim of the input, outside it, non-finite taps) are
+            // only RECORDED in the hot loop -- it stays straight-line code with safe addresses -- and patched
+            // afterwards by affine_edge_voxel.  TZ <= 32, so one bit per step.
+            unsigned rare_mask = 0;
+            if (ZSEP) {
+                // (y, x) part once per column; per step only the z coordinate moves.  The bilinear value of an
+                // input plane at this column's (y, x) is shared by consecutive steps: b0 = plane zc, b1 = plane zc+1.
+                float wy, wx;
+                const int y0 = split_fast(cy, wy), x0 = split_fast(cx, wx);
+                const bool col_fast = (unsigned)(y0 - 1) < hy && (unsigned)(x0 - 1) < hx;
+                const bool col_out = (unsigned)(y0 + 1) > uy || (unsigned)(x0 + 1) > ux;   // certainly outside
+                const float *colq = col_fast ? box + (y0 * pitch + x0 - org_off) : box - oz0 * zs;  // safe when slow
+                int zc = -0x40000000;
+                float b0 = 0.f, b1 = 0.f;
+#pragma unroll 2
+                for (int lz = 0; lz < nz; ++lz) {
+                    float wz;
+                    const int z0 = split_fast(cz, wz);
+                    const bool fast = col_fast && (unsigned)(z0 - 1) < hz;
+                    const int zq = fast ? z0 : oz0;                    // oz0: first plane of the box, always valid
+                    const float *q = colq + zq * zs;
+                    if (zq != zc && zq != zc + 1) {                    // first step, or |z scale| > 1: no reuse
+                        const float a0 = fmaf(wx, q[1] - q[0], q[0]);
+                        const float a1 = fmaf(wx, q[pitch + 1] - q[pitch], q[pitch]);
+                        b1 = fmaf(wy, a1 - a0, a0);
+                        zc = zq - 1;
+                    }
+                    const float *q2 = q + zs;
+                    const float a2 = fmaf(wx, q2[1] - q2[0], q2[0]);
+                    const float a3 = fmaf(wx, q2[pitch + 1] - q2[pitch], q2[pitch]);
+                    const float bnew = fmaf(wy, a3 - a2, a2);
+                    const bool same = zq == zc;
+                    b0 = same ? b0 : b1;
+                    b1 = same ? b1 : bnew;
+                    zc = zq;
+                    const bool outside = col_out || (unsigned)(z0 + 1) > uz;
+                    const float res = outside ? P.cval : fmaf(wz, b1 - b0, b0);
+                    const bool bad = !outside && (!fast || (CLEAN && (__float_as_uint(res) & 0x7f800000u) == 0x7f800000u));
+                    rare_mask |= (unsigned)bad << lz;
+                    __stcs(ptr, res);
+                    ptr += plane;
+                    cz += sz;
+                }
+            } else {
+#pragma unroll 2
+                for (int lz = 0; lz < nz; ++lz) {
+                    float wz, wy, wx;
+                    const int z0 = split_fast(cz, wz), y0 = split_fast(cy, wy), x0 = split_fast(cx, wx);
+                    // 1 <= floor(c) <= dim-3 on every axis: both taps exist, nothing to clamp
+                    const bool fast = (unsigned)(z0 - 1) < hz && (unsigned)(y0 - 1) < hy && (unsigned)(x0 - 1) < hx;
+                    const float *q = fast ? box + (z0 * zs + y0 * pitch + x0 - org_off) : box;
                     const float *q1 = q + pitch, *q2 = q + zs, *q3 = q2 + pitch;
                     const float v000 = q[0], v001 = q[1], v010 = q1[0], v011 = q1[1];
                     const float v100 = q2[0], v101 = q2[1], v110 = q3[0], v111 = q3[1];
@@ -279,14 +329,22 @@ __global__ void __launch_bounds__(kTileThreads, 2)
                     const float a11 = fmaf(wx, v111 - v110, v110);
                     const float b0 = fmaf(wy, a01 - a00, a00);
                     const float b1 = fmaf(wy, a11 - a10, a10);
-                    res = fmaf(wz, b1 - b0, b0);
-                    rare = CLEAN && (__float_as_uint(res) & 0x7f800000u) == 0x7f800000u;  // nan/inf tap
+                    // floor(c) <= -2 or >= dim on some axis: certainly outside, no exact test needed
+                    const bool outside = (unsigned)(z0 + 1) > uz || (unsigned)(y0 + 1) > uy || (unsigned)(x0 + 1) > ux;
+                    const float res = outside ? P.cval : fmaf(wz, b1 - b0, b0);
+                    const bool bad = !outside && (!fast || (CLEAN && (__float_as_uint(res) & 0x7f800000u) == 0x7f800000u));
+                    rare_mask |= (unsigned)bad << lz;
+                    __stcs(ptr, res);
+                    ptr += plane;
+                    cz += sz;
+                    cy += sy;
+                    cx += sx;
                 }
-                if (rare) {
-                    const EdgeCtx E = {P.iz, P.iy, P.ix, P.BZ, P.BY, P.BX, oz0, oy0, ox0, pitch, zs, P.cval, CLEAN};
-                    res = affine_edge_voxel(box, E, cz, cy, cx);
-                }
-                __stcs(row + 32 * i, res);
+            }
+            while (rare_mask) {
+                const int lz = __ffs(rare_mask) - 1;
+                rare_mask &= rare_mask - 1;
+                __stcs(ptr0 + lz * plane, affine_edge_voxel(box, &P, t0z + lz, o1, o2, oz0, oy0, ox0, CLEAN));
             }
         }
     }
@@ -297,7 +355,8 @@ static bool choose_tile(AffineParams &P, int smem_limit, bool tma) {
     static const int cand[][3] = {{8, 16, 64}, {4, 16, 64}, {4, 8, 64},  {2, 16, 64},  {8, 8, 64},   {4, 32, 64},
                                   {2, 32, 64}, {1, 32, 64}, {4, 8, 128}, {2, 16, 128}, {2, 8, 128},  {1, 16, 128},
                                   {4, 32, 32}, {2, 32, 32}, {8, 32, 32}, {1, 64, 64},  {1, 32, 128}, {2, 64, 32},
-                                  {8, 8, 128}, {4, 16, 128}, {8, 16, 128}, {4, 4, 128}, {8, 4, 128}};
+                                  {8, 8, 128}, {4, 16, 128}, {8, 16, 128}, {4, 4, 128}, {8, 4, 128},
+                                  {16, 8, 64}, {16, 16, 64}, {16, 4, 64}, {16, 8, 32}, {16, 16, 32}, {32, 8, 32}};
     double best = 1e300;
     bool found = false;
     int forced[3] = {0, 0, 0};
@@ -370,7 +429,12 @@ extern "C" int shrimpy_affine_device(const float *d_in, float *d_out, int iz, in
     // tensor map constraints hold; otherwise cp.async rows at an odd pitch.
     bool tma = !(force && force[0] == 'c') && std::fabs(M[6]) * 32 <= 4.0 && std::fabs(M[2]) * 32 <= 4.0 &&
                (reinterpret_cast<uintptr_t>(d_in) & 15u) == 0 && ix % 4 == 0 && tensor_map_encoder() != nullptr;
-    if (!want_gather && (choose_tile(P, smem_limit, tma) || (tma && !(tma = false) && choose_tile(P, smem_limit, false)))) {
+    bool tiled = !want_gather && choose_tile(P, smem_limit, tma);
+    if (!tiled && !want_gather && tma) {   // the TMA box did not fit: retry with cp.async staging
+        tma = false;
+        tiled = choose_tile(P, smem_limit, false);
+    }
+    if (tiled) {
         P.tiles_x = (ox + P.TX - 1) / P.TX;
         P.tiles_y = (oy + P.TY - 1) / P.TY;
         P.tiles_z = (oz + P.TZ - 1) / P.TZ;
@@ -391,12 +455,14 @@ extern "C" int shrimpy_affine_device(const float *d_in, float *d_out, int iz, in
             const size_t smem = (size_t)P.BZ * P.BY * P.pitch * sizeof(float) + 128;
             void (*kern)(const CUtensorMap, const AffineParams) = nullptr;
             const int items = P.TX / 32;
-#define SHRIMPY_PICK(I, C, T) affine_tile_kernel<I, C, T>
-#define SHRIMPY_PICK_I(C, T) (items == 1 ? SHRIMPY_PICK(1, C, T) : items == 2 ? SHRIMPY_PICK(2, C, T) : SHRIMPY_PICK(4, C, T))
-            if (nan_to_zero) kern = tma ? SHRIMPY_PICK_I(true, true) : SHRIMPY_PICK_I(true, false);
-            else kern = tma ? SHRIMPY_PICK_I(false, true) : SHRIMPY_PICK_I(false, false);
+            const bool zsep = M[4] == 0.0 && M[8] == 0.0 && !getenv("SHRIMPY_AFFINE_NO_ZSEP");
+#define SHRIMPY_PICK_I(C, T, Z) \
+    (items == 1 ? affine_tile_kernel<1, C, T, Z> : items == 2 ? affine_tile_kernel<2, C, T, Z> : affine_tile_kernel<4, C, T, Z>)
+#define SHRIMPY_PICK_Z(C, T) (zsep ? SHRIMPY_PICK_I(C, T, true) : SHRIMPY_PICK_I(C, T, false))
+            if (nan_to_zero) kern = tma ? SHRIMPY_PICK_Z(true, true) : SHRIMPY_PICK_Z(true, false);
+            else kern = tma ? SHRIMPY_PICK_Z(false, true) : SHRIMPY_PICK_Z(false, false);
+#undef SHRIMPY_PICK_Z
 #undef SHRIMPY_PICK_I
-#undef SHRIMPY_PICK
             if (getenv("SHRIMPY_DEBUG"))
                 fprintf(stderr, "[shrimpy] affine tile T=(%d,%d,%d) B=(%d,%d,%d) pitch=%d tma=%d clean=%d smem=%zu grid=(%d,%d)\n",
                         P.TZ, P.TY, P.TX, P.BZ, P.BY, P.BX, P.pitch, (int)tma, nan_to_zero, smem,

@@ -131,6 +131,26 @@ def test_tile_and_gather_kernels_agree(env, monkeypatch):
         assert_close_range(a, b, AFFINE_TOL, "tile vs gather")
 
 
+@pytest.mark.parametrize("zrow", [(0.6, 0.0, 0.0, 0.3), (1.0, 0.0, 0.0, -2.0), (2.3, 0.0, 0.0, 0.7), (1.1, 0.02, -0.015, 1.5),
+                                  (-0.9, 0.0, 0.0, 30.2)])
+def test_z_separable_matrices(env, zrow, monkeypatch):
+    """Input (y, x) independent of o0 (in-plane registration + z shift/scale/tilt): the kernel reuses the bilinear
+    value of an input plane across consecutive o0; the scan index may advance by 0, 1, 2 or go backwards."""
+    _, _, o, _ = env
+    rng = np.random.default_rng(21)
+    vol = rng.standard_normal((33, 70, 90)).astype(np.float32)
+    th = np.deg2rad(7.0)
+    M = np.array([list(zrow), [0.0, 1.05 * np.cos(th), -np.sin(th), 4.0], [0.0, np.sin(th), 0.95 * np.cos(th), -3.0],
+                  [0, 0, 0, 1.0]])
+    want = o.apply_affine_transform(vol, M, (40, 64, 100), cval=0.5)
+    got = _run(env, vol, M, (40, 64, 100), cval=0.5)
+    assert_close_range(got, want, AFFINE_TOL, f"zsep {zrow}")
+    assert np.array_equal(got == 0.5, want == 0.5)
+    monkeypatch.setenv("SHRIMPY_AFFINE_NO_ZSEP", "1")
+    general = _run(env, vol, M, (40, 64, 100), cval=0.5)
+    assert np.array_equal(got, general)          # same lerp sequence -> bit-identical to the general path
+
+
 def test_medium_volume_vs_c_oracle(env):
     _, _, _, c = env
     rng = np.random.default_rng(8)
