@@ -188,7 +188,7 @@ constexpr int kRowBytes = 128;  // one staged row = 128 B of raw x = one swizzle
 constexpr int kMaxTmaAvg = 4;   // template instantiations exist for n = 1..4
 
 template <typename T, int NAVG>
-__global__ void __launch_bounds__(kTmaThreads, 3)
+__global__ void __launch_bounds__(kTmaThreads, 4)
     deskew_tma_kernel(const __grid_constant__ CUtensorMap tmap, const DeskewParams P) {
     constexpr int EPC = Chunk<T>::kElems;
     constexpr int TX = 8 * EPC;

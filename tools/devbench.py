@@ -140,3 +140,29 @@ if __name__ == "__main__":
                 except Exception as e:
                     print(mode, tile, "failed", str(e)[:80])
         os.environ.pop("SHRIMPY_AFFINE_TILE"); os.environ.pop("SHRIMPY_AFFINE_KERNEL", None)
+    if "copy" in args.cases:
+        n = 1 << 29
+        a = torch.empty(n, dtype=torch.float32, device="cuda").normal_()
+        b = torch.empty_like(a)
+        for _ in range(3):
+            b.copy_(a)
+        torch.cuda.synchronize()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(20)]
+        for x, y in ev:
+            x.record(); b.copy_(a); y.record()
+        torch.cuda.synchronize()
+        ms = np.array([x.elapsed_time(y) for x, y in ev])
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for _ in range(200):
+            b.copy_(a)
+        s1.record(); torch.cuda.synchronize()
+        print(json.dumps({"copy_2GiB_read_plus_2GiB_write": True, "best_gbs": round(2 * n * 4 / ms.min() / 1e6, 1),
+                          "median_gbs": round(2 * n * 4 / np.median(ms) / 1e6, 1),
+                          "sustained_200_back_to_back_gbs": round(200 * 2 * n * 4 / s0.elapsed_time(s1) / 1e6, 1)}), flush=True)
+        # write-only and read-only references
+        s0.record()
+        for _ in range(50):
+            b.fill_(1.0)
+        s1.record(); torch.cuda.synchronize()
+        print(json.dumps({"fill_write_only_gbs": round(50 * n * 4 / s0.elapsed_time(s1) / 1e6, 1)}), flush=True)
