@@ -37,13 +37,14 @@ def _run(env, vol, M, shape, **kw):
     return out.cpu().numpy()
 
 
-@pytest.fixture(params=["tile", "gather"])
+@pytest.fixture(params=["auto", "tile", "gather"])
 def kernel_choice(request, monkeypatch):
-    """Run a test through the shared-memory tiled kernel and through the plain gather kernel."""
-    if request.param == "gather":
-        monkeypatch.setenv("SHRIMPY_AFFINE_KERNEL", "gather")
-    else:
+    """Run a test through the default dispatch (planar kernel for block-diagonal matrices, else the tiled one),
+    through the tiled kernel alone, and through the plain gather kernel."""
+    if request.param == "auto":
         monkeypatch.delenv("SHRIMPY_AFFINE_KERNEL", raising=False)
+    else:
+        monkeypatch.setenv("SHRIMPY_AFFINE_KERNEL", request.param)
     return request.param
 
 
@@ -143,12 +144,52 @@ def test_z_separable_matrices(env, zrow, monkeypatch):
     M = np.array([list(zrow), [0.0, 1.05 * np.cos(th), -np.sin(th), 4.0], [0.0, np.sin(th), 0.95 * np.cos(th), -3.0],
                   [0, 0, 0, 1.0]])
     want = o.apply_affine_transform(vol, M, (40, 64, 100), cval=0.5)
+    auto = _run(env, vol, M, (40, 64, 100), cval=0.5)            # planar kernel when the z row has no tilt
+    assert_close_range(auto, want, AFFINE_TOL, f"auto {zrow}")
+    assert np.array_equal(auto == 0.5, want == 0.5)
+    monkeypatch.setenv("SHRIMPY_AFFINE_KERNEL", "tile")
     got = _run(env, vol, M, (40, 64, 100), cval=0.5)
     assert_close_range(got, want, AFFINE_TOL, f"zsep {zrow}")
     assert np.array_equal(got == 0.5, want == 0.5)
     monkeypatch.setenv("SHRIMPY_AFFINE_NO_ZSEP", "1")
     general = _run(env, vol, M, (40, 64, 100), cval=0.5)
     assert np.array_equal(got, general)          # same lerp sequence -> bit-identical to the general path
+
+
+@pytest.mark.parametrize("angle", [0.0, 7.0, 45.0, 90.0, 93.0, 180.0, 270.0])
+@pytest.mark.parametrize("zscale", [1.0, 0.55, 1.7])
+def test_planar_kernel_in_plane_rotations(env, angle, zscale):
+    """In-plane rotation x scale + z shift/scale (the mantis registration family): planar kernel, lanes along o2
+    for small angles and along o1 (with the shared-memory output transpose) near 90/270 degrees."""
+    _, _, o, _ = env
+    rng = np.random.default_rng(int(angle) + 7)
+    vol = rng.standard_normal((21, 150, 131)).astype(np.float32)
+    vol = np.ascontiguousarray(np.pad(vol, ((0, 0), (0, 0), (0, 1))))          # X = 132, a multiple of 4
+    th = np.deg2rad(angle)
+    cy, cx = 75.0, 66.0
+    R = 1.288 * np.array([[np.cos(th), -np.sin(th)], [np.sin(th), np.cos(th)]])
+    M = np.eye(4)
+    M[0, 0], M[0, 3] = zscale, 0.4
+    M[1:3, 1:3] = R
+    M[1:3, 3] = np.array([cy, cx]) - R @ np.array([50.0, 70.0])
+    shape = (25, 100, 140)
+    want = o.apply_affine_transform(vol, M, shape, cval=-7.0)
+    got = _run(env, vol, M, shape, cval=-7.0)
+    assert_close_range(got, want, AFFINE_TOL, f"planar {angle} {zscale}")
+    assert np.array_equal(got == -7.0, want == -7.0)
+
+
+def test_planar_wide_tiles_identity_and_shift(env):
+    """Wide outputs select the 64-lane tiles of the planar kernel; identity must reproduce the input exactly."""
+    rng = np.random.default_rng(31)
+    vol = rng.standard_normal((20, 96, 512)).astype(np.float32)
+    assert np.array_equal(_run(env, vol, np.eye(4), vol.shape), vol)
+    M = np.eye(4)
+    M[:3, 3] = [2, -3, 5]
+    got = _run(env, vol, M, vol.shape, cval=9.0)
+    want = np.full_like(vol, 9.0)
+    want[:18, 3:, :507] = vol[2:, :93, 5:]
+    assert np.array_equal(got, want)
 
 
 def test_medium_volume_vs_c_oracle(env):
