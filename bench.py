@@ -158,8 +158,8 @@ def run_reference(args):
     cores = os.cpu_count() or 1
     total_passes = args.steps + args.warmup
     rate = cpu_baseline.calibrate_columns_per_second(RAW_SHAPE[0], RAW_SHAPE[1], (ANGLE, RATIO, KEEP, NAVG))
-    # bounded sample: the whole run should end within ~2.5 minutes
-    per_pass_s = max(0.5, 150.0 / max(1, total_passes))
+    # bounded sample: the whole run should end within ~2.5 minutes whatever --steps/--warmup are
+    per_pass_s = max(0.05, 120.0 / max(1, total_passes))
     cols = int(max(1, min(RAW_SHAPE[2] * CHANNELS // cores, rate * per_pass_s * 0.6)))
     walls, out_vox, in_vox = scipy_pass(cols, cores, total_passes)
     timed = walls[args.warmup:]

@@ -43,7 +43,6 @@ struct DeskewParams {
     int nz_cap;    // scan slices per staged row (multiple of 8, <= 256)
     int tiles_x;   // number of raw-x tiles
     int tiles_o2;  // number of o2 tiles
-    int order;     // 0: raw-x tile fastest in blockIdx.x, 1: o2 tile fastest
 };
 
 // Arithmetic shared by every kernel in this file (so that they agree bit for bit):
@@ -177,12 +176,6 @@ struct Chunk<float> {
     }
 };
 
-#ifndef SHRIMPY_STORE_PLAIN
-#define SHRIMPY_STORE(p, v) __stcs((p), (v))   // streaming (evict-first): outputs are never re-read
-#else
-#define SHRIMPY_STORE(p, v) (*(p) = (v))
-#endif
-
 constexpr int kTmaThreads = 256;
 constexpr int kRowBytes = 128;  // one staged row = 128 B of raw x = one swizzle span
 constexpr int kMaxTmaAvg = 4;   // template instantiations exist for n = 1..4
@@ -201,8 +194,10 @@ __global__ void __launch_bounds__(kTmaThreads, 4)
     const uint8_t *tile = smem_dyn + pad;
     const uint32_t region_bytes = (uint32_t)P.nz_cap * kRowBytes;
 
-    const int tx = P.order ? blockIdx.x / P.tiles_o2 : blockIdx.x % P.tiles_x;
-    const int t2 = P.order ? blockIdx.x % P.tiles_o2 : blockIdx.x / P.tiles_x;
+    // raw-x tile fastest: CTAs that run together read adjacent 128-byte segments of the same DRAM rows
+    // (measured: the alternative order makes no difference on B200)
+    const int tx = blockIdx.x % P.tiles_x;
+    const int t2 = blockIdx.x / P.tiles_x;
     const int p = P.p0 + blockIdx.y;
     const int x0 = tx * TX;
     const int c0 = P.cbeg + t2 * P.T2;
@@ -325,7 +320,7 @@ __global__ void __launch_bounds__(kTmaThreads, 4)
             if (xvalid >= EPC) {
 #pragma unroll
                 for (int j = 0; j < EPC; ++j) {
-                    SHRIMPY_STORE(reinterpret_cast<float *>(ptr), r[j]);
+                    __stcs(reinterpret_cast<float *>(ptr), r[j]);   // streaming: outputs are never re-read
                     ptr -= row_bytes;
                     asm volatile("" : "+l"(ptr));  // keep a stepped pointer (2 adds), not base+offset (4)
                 }
@@ -414,7 +409,6 @@ static int launch_tma(const DeskewParams &Pin, cudaStream_t stream, bool *used, 
     }
     P.tiles_x = (P.X + TX - 1) / TX;
     P.tiles_o2 = (P.cend - P.cbeg + P.T2 - 1) / P.T2;
-    P.order = env_int("SHRIMPY_DESKEW_ORDER", 0) ? 1 : 0;
     if ((long long)P.tiles_x * P.tiles_o2 > 2147483647LL) {
         if (required) return fail(SHRIMPY_EINVAL, "deskew: grid too large");
         return SHRIMPY_OK;
