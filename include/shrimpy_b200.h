@@ -120,6 +120,29 @@ int shrimpy_deskew_window_device(const void *d_raw, int raw_dtype, float *d_out,
                                  int64_t out_stride_1, const shrimpy_window *window, int kernel, void *stream);
 
 /*
+ * Bright-field flat-field correction (replaces _LabelfreePreprocessor._flat_field_BF,
+ * shrimpy/preprocessing.py:385-404: static_pattern = volume.quantile(0.5, dim=0);
+ * volume / static_pattern * static_pattern.mean()), expressed as a per-pixel scale field
+ *     scale[y, x] = mean(pattern) / pattern[y, x],   pattern = median over the scan axis
+ * so that it can be fused into the deskew (the step that follows it at preprocessing.py:320-327).
+ *   shrimpy_flatfield_pattern_device  per-pixel median over Z (numpy.median semantics), (Y, X) float32
+ *   shrimpy_flatfield_scale_device    scale field from the pattern; d_scratch = one double of device scratch
+ *   shrimpy_flatfield_apply_device    stand-alone correction: out = raw * scale (float32)
+ *   shrimpy_deskew_flatfield_device   deskew with the scale field applied inside the kernel; the scale field
+ *                                     always refers to the FULL (Y, X) frame, also for windowed calls
+ */
+int shrimpy_flatfield_pattern_device(const void *d_raw, int raw_dtype, float *d_pattern, int Z, int Y, int X,
+                                     int64_t raw_stride_z, int64_t raw_stride_y, void *stream);
+int shrimpy_flatfield_scale_device(const float *d_pattern, int64_t count, float *d_scale, double *d_scratch,
+                                   void *stream);
+int shrimpy_flatfield_apply_device(const void *d_raw, int raw_dtype, const float *d_scale, float *d_out, int Z, int Y,
+                                   int X, void *stream);
+int shrimpy_deskew_flatfield_device(const void *d_raw, int raw_dtype, const float *d_scale, float *d_out, int Z, int Y,
+                                    int X, int Xp, int n_avg, double m00, double m02, double shift, float cval,
+                                    int64_t raw_stride_z, int64_t raw_stride_y, const shrimpy_window *window,
+                                    int kernel, void *stream);
+
+/*
  * Device-resident trilinear resample with a 3x4 (row-major, 12 doubles)
  * output-index -> input-index matrix in ZYX voxel units (the registration
  * resample named by BASELINE.json configs[2]; upstream

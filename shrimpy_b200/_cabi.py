@@ -27,6 +27,10 @@ EXPORTS = (
     "shrimpy_deskew_device",
     "shrimpy_deskew_window_needs",
     "shrimpy_deskew_window_device",
+    "shrimpy_flatfield_pattern_device",
+    "shrimpy_flatfield_scale_device",
+    "shrimpy_flatfield_apply_device",
+    "shrimpy_deskew_flatfield_device",
     "shrimpy_affine_device",
     "shrimpy_min_device",
     "shrimpy_pipeline_create",
@@ -79,6 +83,16 @@ def _declare(lib) -> None:
     lib.shrimpy_deskew_window_needs.restype = c_int
     lib.shrimpy_deskew_window_needs.argtypes = [c_int, c_int, c_int, c_dbl, c_dbl, c_dbl, c_int, c_int, c_int, c_int,
                                                 ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32)]
+    lib.shrimpy_flatfield_pattern_device.restype = c_int
+    lib.shrimpy_flatfield_pattern_device.argtypes = [c_vp, c_int, c_vp, c_int, c_int, c_int, c_i64, c_i64, c_vp]
+    lib.shrimpy_flatfield_scale_device.restype = c_int
+    lib.shrimpy_flatfield_scale_device.argtypes = [c_vp, c_i64, c_vp, c_vp, c_vp]
+    lib.shrimpy_flatfield_apply_device.restype = c_int
+    lib.shrimpy_flatfield_apply_device.argtypes = [c_vp, c_int, c_vp, c_vp, c_int, c_int, c_int, c_vp]
+    lib.shrimpy_deskew_flatfield_device.restype = c_int
+    lib.shrimpy_deskew_flatfield_device.argtypes = [c_vp, c_int, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int,
+                                                    c_dbl, c_dbl, c_dbl, c_flt, c_i64, c_i64,
+                                                    ctypes.POINTER(Window), c_int, c_vp]
     lib.shrimpy_affine_device.restype = c_int
     lib.shrimpy_affine_device.argtypes = [c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int,
                                           ctypes.POINTER(c_dbl), c_flt, c_int, c_vp]

@@ -39,6 +39,7 @@ struct DeskewParams {
     double m00, m02, shift;
     float cval;
     float inv_n;
+    const float *scale;  // optional flat-field scale field (Y, X) of the FULL stack, or nullptr
     int T2;        // o2 extent of a tile (32, 64, 128 or 256)
     int nz_cap;    // scan slices per staged row (multiple of 8, <= 256)
     int tiles_x;   // number of raw-x tiles
@@ -52,6 +53,10 @@ struct DeskewParams {
 //   W   = fma(u_{n-1}, d_{n-1}, ... fma(u_1, d_1, u_0 * d_0))
 //   out = n == 1 ? fma(w_0, d_0, a_0) : fma(S, 1/n, W);   every row outside -> exactly cval
 // For uint16 data S is an exact integer, so only W and the final scale round (float32).
+// With a flat-field scale field s[y,x] (shrimpy/preprocessing.py:385-404 fused in; the deskew interpolates
+// along z only, so the per-pixel scale commutes with it):
+//   t_k = fma(w_k, d_k, a_k),  g_k = s[y_k, x] * (1/n)   (outside row: t_k = cval, g_k = 1/n)
+//   out = fma(g_{n-1}, t_{n-1}, ... g_0 * t_0);           every row outside -> exactly cval
 
 __device__ __forceinline__ double scan_coord(double base, int o2, double m02) {
     // scipy accumulates shift + o0*M00 first, then + o2*M02, each product and sum rounded separately.
@@ -67,7 +72,7 @@ __global__ void __launch_bounds__(128) deskew_direct_kernel(const DeskewParams P
     const T *__restrict__ raw = static_cast<const T *>(P.raw);
     const long long xoff = P.X - 1 - o1;
     const double zmax = (double)(P.Z - 1);
-    float S = 0.f, W = 0.f, one = P.cval;
+    float S = 0.f, W = 0.f, one = P.cval, G = 0.f;
     int n_in = 0;
     for (int k = 0; k < P.n; ++k) {
         const int o0 = min(P.n * p + k, P.Y - 1);
@@ -89,8 +94,14 @@ __global__ void __launch_bounds__(128) deskew_direct_kernel(const DeskewParams P
         S = (k == 0) ? a : S + a;
         W = (k == 0) ? u * d : fmaf(u, d, W);
         if (k == 0) one = fmaf(w, d, a);
+        if (P.scale) {
+            const bool in = z >= 0.0 && z <= zmax;
+            const float g = in ? __ldg(P.scale + (long long)(P.Y - 1 - o0) * P.X + xoff) * P.inv_n : P.inv_n;
+            const float t = fmaf(w, d, a);
+            G = (k == 0) ? g * t : fmaf(g, t, G);
+        }
     }
-    const float r = (n_in == 0) ? P.cval : (P.n == 1) ? one : fmaf(S, P.inv_n, W);
+    const float r = (n_in == 0) ? P.cval : P.scale ? G : (P.n == 1) ? one : fmaf(S, P.inv_n, W);
     __stcs(P.out + (long long)(p - P.p0) * P.out_sp + (long long)o1 * P.out_s1 + (o2 - P.cbeg), r);
 }
 
@@ -149,6 +160,13 @@ struct Chunk<uint16_t> {
     }
 };
 
+// flat-field variant of the fast path (all rows inside): g points at this chunk's kElems scale values of row k,
+// already multiplied by 1/n, in shared memory (same address for every lane: broadcast reads)
+template <typename T, int NAVG>
+__device__ __forceinline__ void fast_scaled(const uint8_t *tile, const uint32_t *off0, const uint32_t *off1,
+                                            const uint32_t *sw0, const uint32_t *sw1, const float *w,
+                                            const float *g, int g_row_stride, uint32_t cbyte, float *out);
+
 template <>
 struct Chunk<float> {
     static constexpr int kElems = 4;
@@ -176,15 +194,48 @@ struct Chunk<float> {
     }
 };
 
+template <typename T, int NAVG>
+__device__ __forceinline__ void fast_scaled(const uint8_t *tile, const uint32_t *off0, const uint32_t *off1,
+                                            const uint32_t *sw0, const uint32_t *sw1, const float *w,
+                                            const float *g, int g_row_stride, uint32_t cbyte, float *out) {
+    constexpr int EPC = Chunk<T>::kElems;
+#pragma unroll
+    for (int k = 0; k < NAVG; ++k) {
+        const uint4 A = *reinterpret_cast<const uint4 *>(tile + off0[k] + (cbyte ^ sw0[k]));
+        const uint4 B = *reinterpret_cast<const uint4 *>(tile + off1[k] + (cbyte ^ sw1[k]));
+        float gk[EPC];
+#pragma unroll
+        for (int j = 0; j < EPC; j += 4) {
+            const float4 v = *reinterpret_cast<const float4 *>(g + k * g_row_stride + j);
+            gk[j] = v.x; gk[j + 1] = v.y; gk[j + 2] = v.z; gk[j + 3] = v.w;
+        }
+#pragma unroll
+        for (int j = 0; j < EPC; ++j) {
+            float a, d;
+            if (sizeof(T) == 2) {
+                const uint32_t am = Chunk<uint16_t>::magic(A, j), bm = Chunk<uint16_t>::magic(B, j);
+                d = __uint_as_float(bm) - __uint_as_float(am);
+                a = __uint_as_float(am) - 8388608.0f;
+            } else {
+                a = Chunk<float>::get(A, j);
+                d = Chunk<float>::get(B, j) - a;
+            }
+            const float t = fmaf(w[k], d, a);
+            out[j] = (k == 0) ? gk[j] * t : fmaf(gk[j], t, out[j]);
+        }
+    }
+}
+
 constexpr int kTmaThreads = 256;
 constexpr int kRowBytes = 128;  // one staged row = 128 B of raw x = one swizzle span
 constexpr int kMaxTmaAvg = 4;   // template instantiations exist for n = 1..4
 
-template <typename T, int NAVG>
+template <typename T, int NAVG, bool SCALED>
 __global__ void __launch_bounds__(kTmaThreads, 4)
     deskew_tma_kernel(const __grid_constant__ CUtensorMap tmap, const DeskewParams P) {
     constexpr int EPC = Chunk<T>::kElems;
     constexpr int TX = 8 * EPC;
+    __shared__ __align__(16) float s_scale[SCALED ? NAVG * TX : 4];   // scale * (1/n) of this tile's rows
 
     extern __shared__ uint8_t smem_dyn[];
     __shared__ __align__(8) uint64_t bar;
@@ -238,7 +289,14 @@ __global__ void __launch_bounds__(kTmaThreads, 4)
         __syncwarp();
         if (need) tma_load_3d(smem_u32(tile) + lane * region_bytes, &tmap, x0, yrow, zlo - P.z_org, &bar);
     }
-    __syncthreads();  // row ranges and the initialised barrier visible to everyone
+    if (SCALED) {
+        for (int i = threadIdx.x; i < NAVG * TX; i += kTmaThreads) {
+            const int k = i / TX, x = x0 + (i - k * TX);
+            const int o0 = min(NAVG * p + k, P.Y - 1);
+            s_scale[i] = (x < P.X) ? __ldg(P.scale + (long long)(P.Y - 1 - o0) * P.X + x) * P.inv_n : 0.f;
+        }
+    }
+    __syncthreads();  // row ranges, scale tile and the initialised barrier visible to everyone
     const bool any_need = s_need != 0;
 
     // Per-thread column state while the boxes are in flight.
@@ -286,13 +344,14 @@ __global__ void __launch_bounds__(kTmaThreads, 4)
     for (int c = part; c < 8; c += parts) {
         float r[EPC];
         if (warp_all_in) {
-            Chunk<T>::template fast<NAVG>(tile, off0, off1, sw0, sw1, w, u, (uint32_t)c << 4, P.inv_n, r);
+            if (SCALED) fast_scaled<T, NAVG>(tile, off0, off1, sw0, sw1, w, s_scale + c * EPC, TX, (uint32_t)c << 4, r);
+            else Chunk<T>::template fast<NAVG>(tile, off0, off1, sw0, sw1, w, u, (uint32_t)c << 4, P.inv_n, r);
         } else if (warp_none_in) {
 #pragma unroll
             for (int j = 0; j < EPC; ++j) r[j] = P.cval;
         } else {
             // boundary warps: some rows / lanes outside
-            float S[EPC], W[EPC], one[EPC];
+            float S[EPC], W[EPC], one[EPC], G[EPC];
 #pragma unroll
             for (int k = 0; k < NAVG; ++k) {
                 uint4 A = make_uint4(0, 0, 0, 0), B = A;
@@ -307,11 +366,16 @@ __global__ void __launch_bounds__(kTmaThreads, 4)
                     S[j] = (k == 0) ? a : S[j] + a;
                     W[j] = (k == 0) ? u[k] * d : fmaf(u[k], d, W[j]);   // w = u = 0 outside
                     if (k == 0) one[j] = fmaf(w[k], d, a);
+                    if (SCALED) {
+                        const float g = inside[k] ? s_scale[k * TX + c * EPC + j] : P.inv_n;
+                        const float t = fmaf(w[k], d, a);
+                        G[j] = (k == 0) ? g * t : fmaf(g, t, G[j]);
+                    }
                 }
             }
 #pragma unroll
             for (int j = 0; j < EPC; ++j)
-                r[j] = none_in ? P.cval : (NAVG == 1) ? one[j] : fmaf(S[j], P.inv_n, W[j]);
+                r[j] = none_in ? P.cval : SCALED ? G[j] : (NAVG == 1) ? one[j] : fmaf(S[j], P.inv_n, W[j]);
         }
         if (col_ok) {
             const int xc = x0 + c * EPC;
@@ -358,7 +422,7 @@ static int launch_direct(const DeskewParams &Pin, cudaStream_t stream) {
 
 template <typename T, int NAVG>
 static int launch_tma_n(const CUtensorMap &tmap, const DeskewParams &P, size_t smem, cudaStream_t stream) {
-    auto kern = deskew_tma_kernel<T, NAVG>;
+    auto kern = P.scale ? deskew_tma_kernel<T, NAVG, true> : deskew_tma_kernel<T, NAVG, false>;
     if (smem + 1024 > 48 * 1024)  // static smem counts against the 48 KB default as well
         SHRIMPY_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<dim3((unsigned)((long long)P.tiles_x * P.tiles_o2), (unsigned)P.pcount), kTmaThreads, smem, stream>>>(tmap, P);
@@ -495,11 +559,10 @@ extern "C" int shrimpy_deskew_window_needs(int Z, int Y, int n_avg, double m00, 
     return SHRIMPY_OK;
 }
 
-extern "C" int shrimpy_deskew_window_device(const void *d_raw, int raw_dtype, float *d_out, int Z, int Y, int X,
-                                            int Xp, int n_avg, double m00, double m02, double shift, float cval,
-                                            int64_t raw_stride_z, int64_t raw_stride_y, int64_t out_stride_p,
-                                            int64_t out_stride_1, const shrimpy_window *win, int kernel,
-                                            void *stream) {
+static int deskew_window_impl(const void *d_raw, int raw_dtype, float *d_out, int Z, int Y, int X, int Xp, int n_avg,
+                              double m00, double m02, double shift, float cval, int64_t raw_stride_z,
+                              int64_t raw_stride_y, int64_t out_stride_p, int64_t out_stride_1,
+                              const shrimpy_window *win, const float *d_scale, int kernel, void *stream) {
     if (Z <= 0 || Y <= 0 || X <= 0 || Xp < 0 || n_avg <= 0)
         return fail(SHRIMPY_EINVAL, "deskew: bad shape Z=%d Y=%d X=%d Xp=%d n=%d", Z, Y, X, Xp, n_avg);
     if (raw_dtype != SHRIMPY_U16 && raw_dtype != SHRIMPY_F32)
@@ -544,8 +607,27 @@ extern "C" int shrimpy_deskew_window_device(const void *d_raw, int raw_dtype, fl
     P.m00 = m00; P.m02 = m02; P.shift = shift;
     P.cval = cval;
     P.inv_n = 1.0f / (float)n_avg;
+    P.scale = d_scale;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     return raw_dtype == SHRIMPY_U16 ? deskew_dispatch<uint16_t>(P, kernel, s) : deskew_dispatch<float>(P, kernel, s);
+}
+
+extern "C" int shrimpy_deskew_window_device(const void *d_raw, int raw_dtype, float *d_out, int Z, int Y, int X,
+                                            int Xp, int n_avg, double m00, double m02, double shift, float cval,
+                                            int64_t raw_stride_z, int64_t raw_stride_y, int64_t out_stride_p,
+                                            int64_t out_stride_1, const shrimpy_window *win, int kernel,
+                                            void *stream) {
+    return deskew_window_impl(d_raw, raw_dtype, d_out, Z, Y, X, Xp, n_avg, m00, m02, shift, cval, raw_stride_z,
+                              raw_stride_y, out_stride_p, out_stride_1, win, nullptr, kernel, stream);
+}
+
+extern "C" int shrimpy_deskew_flatfield_device(const void *d_raw, int raw_dtype, const float *d_scale, float *d_out,
+                                               int Z, int Y, int X, int Xp, int n_avg, double m00, double m02,
+                                               double shift, float cval, int64_t raw_stride_z, int64_t raw_stride_y,
+                                               const shrimpy_window *win, int kernel, void *stream) {
+    if (!d_scale) return fail(SHRIMPY_EINVAL, "deskew: null flat-field scale field");
+    return deskew_window_impl(d_raw, raw_dtype, d_out, Z, Y, X, Xp, n_avg, m00, m02, shift, cval, raw_stride_z,
+                              raw_stride_y, 0, 0, win, d_scale, kernel, stream);
 }
 
 extern "C" int shrimpy_deskew_device(const void *d_raw, int raw_dtype, float *d_out, int Z, int Y, int X, int Xp,

@@ -2,7 +2,8 @@
 
     python tests/golden/make_golden.py
 
-Two fixtures:
+Three fixtures (the third, ``flatfield.npz``, holds outputs of the unmodified reference method
+``_LabelfreePreprocessor._flat_field_BF`` -- a result pinned by the reference itself):
 
 ``reference_boundary.json``
     Produced by importing the UNMODIFIED reference module ``/root/reference/shrimpy/preprocessing.py``
@@ -136,6 +137,30 @@ def voxel_fixture():
     print("wrote deskew_small.npz", sum(v.nbytes for v in arrays.values()), "bytes raw")
 
 
+def flatfield_fixture():
+    """Golden output of the UNMODIFIED reference method _LabelfreePreprocessor._flat_field_BF (pure torch, CPU)."""
+    ref = Path("/root/reference")
+    if not ref.exists():
+        raise SystemExit("/root/reference is required to regenerate flatfield.npz")
+    sys.path.insert(0, str(ref))
+    import torch
+    from shrimpy import preprocessing as ref_pre
+
+    pre = ref_pre._LabelfreePreprocessor.__new__(ref_pre._LabelfreePreprocessor)   # the method uses no instance state
+    rng = np.random.default_rng(3)
+    arrays = {}
+    for name, shape in (("even_z", (8, 6, 10)), ("odd_z", (9, 5, 12)), ("tall", (70, 4, 66))):
+        vol = rng.integers(80, 600, shape).astype(np.float32)
+        # a smooth illumination pattern on top, so that the correction is not the identity
+        yy, xx = np.meshgrid(np.linspace(0.7, 1.3, shape[1]), np.linspace(0.8, 1.2, shape[2]), indexing="ij")
+        vol = np.round(vol * (yy * xx)[None]).astype(np.float32)
+        arrays[f"{name}__vol"] = vol.astype(np.uint16)
+        arrays[f"{name}__out"] = pre._flat_field_BF(torch.as_tensor(vol, dtype=torch.float32)).numpy()
+    np.savez_compressed(HERE / "flatfield.npz", **arrays)
+    print("wrote flatfield.npz", sum(v.nbytes for v in arrays.values()), "bytes raw")
+
+
 if __name__ == "__main__":
     voxel_fixture()
     boundary_fixture()
+    flatfield_fixture()

@@ -140,3 +140,17 @@ def test_golden_vectors():
         M, want = data[f"affine_{tag}__matrix"], data[f"affine_{tag}__out"]
         assert np.array_equal(o.apply_affine_transform(vol, M, want.shape), want)
         assert np.max(np.abs(c_oracle.apply_affine_transform(vol, M, want.shape) - want)) <= 1e-6
+
+
+def test_flatfield_oracle_matches_the_reference_golden():
+    """tests/golden/flatfield.npz was produced by the UNMODIFIED reference method
+    _LabelfreePreprocessor._flat_field_BF (shrimpy/preprocessing.py:385-404) -- a reference-pinned result."""
+    from oracle import flatfield_oracle as ff
+
+    data = np.load(GOLDEN / "flatfield.npz")
+    for name in ("even_z", "odd_z", "tall"):
+        vol, want = data[f"{name}__vol"], data[f"{name}__out"]
+        got = ff.flat_field_BF(vol)
+        assert got.shape == want.shape and got.dtype == np.float32
+        # the reference test's own tolerance is atol=1e-2 (tests/test_preprocessing.py:162); we hold 1e-3
+        assert np.max(np.abs(got - want)) <= 1e-3

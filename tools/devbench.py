@@ -166,3 +166,32 @@ if __name__ == "__main__":
             b.fill_(1.0)
         s1.record(); torch.cuda.synchronize()
         print(json.dumps({"fill_write_only_gbs": round(50 * n * 4 / s0.elapsed_time(s1) / 1e6, 1)}), flush=True)
+    if "flatfield" in args.cases:
+        from shrimpy_b200 import flatfield as ffm
+        shape = (600, 300, 2048)
+        gen = torch.Generator(device="cuda").manual_seed(3)
+        raw = torch.randint(2000, 9000, shape, dtype=torch.int32, device="cuda", generator=gen).to(torch.uint16)
+        g = sb.deskew_geometry(shape, 30.0, 0.39, False, 3)
+        out = torch.empty(g.out_shape, dtype=torch.float32, device="cuda")
+
+        def timeit(fn, reps=10):
+            for _ in range(2):
+                fn()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(reps):
+                fn()
+            b.record(); torch.cuda.synchronize()
+            return a.elapsed_time(b) / reps
+
+        scale = ffm.flat_field_scale(raw)
+        res = {"pattern_ms": timeit(lambda: ffm.flat_field_pattern(raw)),
+               "scale_total_ms": timeit(lambda: ffm.flat_field_scale(raw)),
+               "standalone_flatfield_ms": timeit(lambda: ffm.flat_field_BF(raw), reps=5),
+               "fused_deskew_given_scale_ms": timeit(lambda: ffm.deskew_flat_field_zyx(raw, 30.0, 0.39, False, 3, scale=scale, out=out)),
+               "fused_total_ms": timeit(lambda: ffm.deskew_flat_field_zyx(raw, 30.0, 0.39, False, 3, out=out)),
+               "plain_deskew_ms": timeit(lambda: sb.deskew_zyx(raw, 30.0, 0.39, False, 3, out=out))}
+        ff32 = ffm.flat_field_BF(raw)
+        res["two_step_ms"] = res["standalone_flatfield_ms"] + timeit(lambda: sb.deskew_zyx(ff32, 30.0, 0.39, False, 3, out=out))
+        print(json.dumps({k: round(v, 4) for k, v in res.items()}), flush=True)
