@@ -152,6 +152,17 @@ int shrimpy_deskew_flatfield_device(const void *d_raw, int raw_dtype, const floa
 int shrimpy_affine_device(const float *d_in, float *d_out, int iz, int iy, int ix, int oz, int oy, int ox,
                           const double M[12], float cval, int nan_to_zero, void *stream);
 
+/*
+ * Reductions over a deskewed float32 volume used by the tracking step that consumes it
+ * (shrimpy/dynatrack/tracking.py:572-649): value range, torch.histc-style 256-bin histogram for the background
+ * percentile, and the sums of the intensity centre of mass with weights w = max(v - background, 0):
+ *   d_sums4 = (sum w, sum w*z, sum w*y, sum w*x) in float64.  One streaming pass each.
+ */
+int shrimpy_minmax_device(const float *d_data, int64_t count, float *d_out2, void *stream);
+int shrimpy_hist256_device(const float *d_data, int64_t count, float vmin, float vmax, uint64_t *d_hist, void *stream);
+int shrimpy_center_of_mass_device(const float *d_data, int Z, int Y, int X, float background, double *d_sums4,
+                                  void *stream);
+
 /* min over a device array (for cval = min(raw), the scipy-generation default). */
 int shrimpy_min_device(const void *d_raw, int raw_dtype, int64_t count, float *d_result, void *stream);
 

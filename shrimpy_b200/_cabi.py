@@ -32,6 +32,9 @@ EXPORTS = (
     "shrimpy_flatfield_apply_device",
     "shrimpy_deskew_flatfield_device",
     "shrimpy_affine_device",
+    "shrimpy_minmax_device",
+    "shrimpy_hist256_device",
+    "shrimpy_center_of_mass_device",
     "shrimpy_min_device",
     "shrimpy_pipeline_create",
     "shrimpy_pipeline_destroy",
@@ -96,6 +99,12 @@ def _declare(lib) -> None:
     lib.shrimpy_affine_device.restype = c_int
     lib.shrimpy_affine_device.argtypes = [c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int,
                                           ctypes.POINTER(c_dbl), c_flt, c_int, c_vp]
+    lib.shrimpy_minmax_device.restype = c_int
+    lib.shrimpy_minmax_device.argtypes = [c_vp, c_i64, c_vp, c_vp]
+    lib.shrimpy_hist256_device.restype = c_int
+    lib.shrimpy_hist256_device.argtypes = [c_vp, c_i64, c_flt, c_flt, c_vp, c_vp]
+    lib.shrimpy_center_of_mass_device.restype = c_int
+    lib.shrimpy_center_of_mass_device.argtypes = [c_vp, c_int, c_int, c_int, c_flt, c_vp, c_vp]
     lib.shrimpy_min_device.restype = c_int
     lib.shrimpy_min_device.argtypes = [c_vp, c_int, c_i64, c_vp, c_vp]
     lib.shrimpy_pipeline_create.restype = c_int

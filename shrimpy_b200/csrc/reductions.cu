@@ -1,0 +1,164 @@
+// Post-deskew reductions used by the tracking step that follows the deskew:
+//   min/max                     -> range of the histogram          (shrimpy/dynatrack/tracking.py:583-584)
+//   256-bin histogram           -> background percentile           (tracking.py:587-595, torch.histc semantics)
+//   intensity centre of mass    -> sum w, sum w*z, sum w*y, sum w*x with w = max(v - background, 0)
+//                                                                    (tracking.py:626-649)
+// Each is one streaming pass over the float32 volume (HBM-bound: 4 bytes per voxel).
+#include "common.cuh"
+
+#include <algorithm>
+#include <cfloat>
+
+namespace shrimpy {
+
+__device__ __forceinline__ unsigned ordered_key(float f) {
+    const unsigned u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ordered_value(unsigned k) {
+    return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
+__global__ void minmax_init_kernel(unsigned *slots) {
+    slots[0] = 0xffffffffu;
+    slots[1] = 0u;
+}
+
+__global__ void __launch_bounds__(256) minmax_kernel(const float4 *__restrict__ v4, const float *__restrict__ v,
+                                                     long long n4, long long n, unsigned *slots) {
+    float lo = FLT_MAX, hi = -FLT_MAX;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        const float4 a = __ldg(v4 + i);
+        lo = fminf(fminf(lo, a.x), fminf(a.y, fminf(a.z, a.w)));
+        hi = fmaxf(fmaxf(hi, a.x), fmaxf(a.y, fmaxf(a.z, a.w)));
+    }
+    for (long long i = 4 * n4 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        lo = fminf(lo, v[i]);
+        hi = fmaxf(hi, v[i]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(slots, ordered_key(lo));
+        atomicMax(slots + 1, ordered_key(hi));
+    }
+}
+
+__global__ void minmax_finish_kernel(const unsigned *slots, float *out) {
+    out[0] = ordered_value(slots[0]);
+    out[1] = ordered_value(slots[1]);
+}
+
+// torch.histc: bin = floor((v - min) / (max - min) * nbins), v == max falls in the last bin, values outside ignored.
+// One sub-histogram per warp in shared memory keeps the atomics short.
+__global__ void __launch_bounds__(256) hist256_kernel(const float *__restrict__ v, long long n, float vmin, float vmax,
+                                                      unsigned long long *hist) {
+    __shared__ unsigned sub[8][256];
+    for (int i = threadIdx.x; i < 8 * 256; i += 256) (&sub[0][0])[i] = 0u;
+    __syncthreads();
+    const float range = vmax - vmin;
+    unsigned *mine = sub[threadIdx.x >> 5];
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const float x = __ldg(v + i);
+        if (x >= vmin && x <= vmax) {
+            int b = (int)((x - vmin) / range * 256.0f);
+            b = min(b, 255);
+            atomicAdd(mine + b, 1u);
+        }
+    }
+    __syncthreads();
+    for (int b = threadIdx.x; b < 256; b += 256) {
+        unsigned long long t = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += sub[w][b];
+        if (t) atomicAdd(hist + b, t);
+    }
+}
+
+// sums[0..3] += (sum w, sum w*z, sum w*y, sum w*x); one (z, y) row per warp iteration, lanes along x
+__global__ void __launch_bounds__(256) com_kernel(const float *__restrict__ v, int Z, int Y, int X, float background,
+                                                  double *sums) {
+    double s = 0.0, sz = 0.0, sy = 0.0, sx = 0.0;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long rows = (long long)Z * Y;
+    for (long long r = (long long)blockIdx.x * 8 + warp; r < rows; r += (long long)gridDim.x * 8) {
+        const int z = (int)(r / Y), y = (int)(r - (long long)z * Y);
+        const float *row = v + r * X;
+        float w_row = 0.f, wx_row = 0.f;   // float32 within one row (<= 32 * X/32 terms per lane), float64 across rows
+        for (int x = lane; x < X; x += 32) {
+            const float w = fmaxf(__ldg(row + x) - background, 0.f);
+            w_row += w;
+            wx_row = fmaf(w, (float)x, wx_row);
+        }
+        s += (double)w_row;
+        sx += (double)wx_row;
+        sz += (double)w_row * z;
+        sy += (double)w_row * y;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        sz += __shfl_xor_sync(0xffffffffu, sz, o);
+        sy += __shfl_xor_sync(0xffffffffu, sy, o);
+        sx += __shfl_xor_sync(0xffffffffu, sx, o);
+    }
+    if (lane == 0) {
+        atomicAdd(sums + 0, s);
+        atomicAdd(sums + 1, sz);
+        atomicAdd(sums + 2, sy);
+        atomicAdd(sums + 3, sx);
+    }
+}
+
+}  // namespace shrimpy
+
+using namespace shrimpy;
+
+static int grid_for(long long work_items, int per_block) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return (int)std::min<long long>((work_items + per_block - 1) / per_block, (long long)sm_count(dev) * 8);
+}
+
+extern "C" int shrimpy_minmax_device(const float *d_data, int64_t count, float *d_out2, void *stream) {
+    if (!d_data || !d_out2 || count <= 0) return fail(SHRIMPY_EINVAL, "minmax: bad arguments");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    unsigned *slots = reinterpret_cast<unsigned *>(d_out2);   // the result words double as the ordered-key scratch
+    const bool vec = (reinterpret_cast<uintptr_t>(d_data) & 15u) == 0;
+    const long long n4 = vec ? count / 4 : 0;
+    minmax_init_kernel<<<1, 1, 0, s>>>(slots);
+    minmax_kernel<<<grid_for(std::max<long long>(n4, count / 4 + 1), 256), 256, 0, s>>>(
+        reinterpret_cast<const float4 *>(d_data), d_data, n4, count, slots);
+    minmax_finish_kernel<<<1, 1, 0, s>>>(slots, d_out2);
+    count_launch(3);
+    SHRIMPY_CUDA_TRY(cudaGetLastError());
+    return SHRIMPY_OK;
+}
+
+extern "C" int shrimpy_hist256_device(const float *d_data, int64_t count, float vmin, float vmax, uint64_t *d_hist,
+                                      void *stream) {
+    if (!d_data || !d_hist || count <= 0 || !(vmax > vmin)) return fail(SHRIMPY_EINVAL, "hist256: bad arguments");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    SHRIMPY_CUDA_TRY(cudaMemsetAsync(d_hist, 0, 256 * sizeof(uint64_t), s));
+    hist256_kernel<<<grid_for(count, 256 * 16), 256, 0, s>>>(d_data, count, vmin, vmax,
+                                                              reinterpret_cast<unsigned long long *>(d_hist));
+    count_launch();
+    SHRIMPY_CUDA_TRY(cudaGetLastError());
+    return SHRIMPY_OK;
+}
+
+extern "C" int shrimpy_center_of_mass_device(const float *d_data, int Z, int Y, int X, float background, double *d_sums4,
+                                             void *stream) {
+    if (!d_data || !d_sums4 || Z <= 0 || Y <= 0 || X <= 0) return fail(SHRIMPY_EINVAL, "center_of_mass: bad arguments");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    SHRIMPY_CUDA_TRY(cudaMemsetAsync(d_sums4, 0, 4 * sizeof(double), s));
+    com_kernel<<<grid_for((long long)Z * Y, 8 * 4), 256, 0, s>>>(d_data, Z, Y, X, background, d_sums4);
+    count_launch();
+    SHRIMPY_CUDA_TRY(cudaGetLastError());
+    return SHRIMPY_OK;
+}

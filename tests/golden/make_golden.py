@@ -2,8 +2,9 @@
 
     python tests/golden/make_golden.py
 
-Three fixtures (the third, ``flatfield.npz``, holds outputs of the unmodified reference method
-``_LabelfreePreprocessor._flat_field_BF`` -- a result pinned by the reference itself):
+Four fixtures (``flatfield.npz`` and ``reductions.json`` hold outputs of unmodified reference functions --
+``_LabelfreePreprocessor._flat_field_BF``, ``tracking._percentile``, ``tracking._intensity_center_of_mass`` --
+i.e. results pinned by the reference itself):
 
 ``reference_boundary.json``
     Produced by importing the UNMODIFIED reference module ``/root/reference/shrimpy/preprocessing.py``
@@ -160,7 +161,34 @@ def flatfield_fixture():
     print("wrote flatfield.npz", sum(v.nbytes for v in arrays.values()), "bytes raw")
 
 
+def reductions_fixture():
+    """Golden outputs of the UNMODIFIED reference helpers _percentile and _intensity_center_of_mass
+    (shrimpy/dynatrack/tracking.py:572-649; pure torch, run on CPU)."""
+    ref = Path("/root/reference")
+    if not ref.exists():
+        raise SystemExit("/root/reference is required to regenerate reductions.json")
+    sys.path.insert(0, str(ref))
+    import torch
+    from shrimpy.dynatrack import tracking as ref_tr
+
+    cases = []
+    for seed, shape in ((0, (12, 20, 33)), (1, (7, 64, 50)), (2, (30, 9, 130))):
+        rng = np.random.default_rng(seed)
+        vol = rng.gamma(2.0, 300.0, size=shape).astype(np.float32)
+        vol[shape[0] // 2, shape[1] // 3, shape[2] // 4] += 50000.0      # a bright blob pulls the centroid
+        t = torch.as_tensor(vol)
+        case = {"seed": seed, "shape": list(shape), "percentiles": {}, "com": {}}
+        for p in (1.0, 25.0, 50.0, 90.0, 99.5):
+            case["percentiles"][str(p)] = ref_tr._percentile(t, p)
+        for bg in (0.0, 400.0, 1e9):
+            case["com"][str(bg)] = [float(v) for v in ref_tr._intensity_center_of_mass(t, background=bg)]
+        cases.append(case)
+    (HERE / "reductions.json").write_text(json.dumps(cases, indent=1) + "\n")
+    print("wrote reductions.json", len(cases), "cases")
+
+
 if __name__ == "__main__":
     voxel_fixture()
     boundary_fixture()
     flatfield_fixture()
+    reductions_fixture()

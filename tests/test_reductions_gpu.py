@@ -1,0 +1,76 @@
+"""Tracking reductions over a deskewed volume against goldens produced by the UNMODIFIED reference helpers
+(shrimpy/dynatrack/tracking.py:572-649, see tests/golden/make_golden.py)."""
+
+import json
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+GOLDEN = Path(__file__).parent / "golden"
+
+
+def _volume(seed, shape):
+    rng = np.random.default_rng(seed)
+    vol = rng.gamma(2.0, 300.0, size=shape).astype(np.float32)
+    vol[shape[0] // 2, shape[1] // 3, shape[2] // 4] += 50000.0
+    return vol
+
+
+def test_percentile_and_center_of_mass_match_the_reference_golden():
+    import torch
+
+    from shrimpy_b200 import reductions as red
+
+    for case in json.loads((GOLDEN / "reductions.json").read_text()):
+        vol = _volume(case["seed"], tuple(case["shape"]))
+        t = torch.from_numpy(vol).cuda()
+        lo, hi = red.value_range(t)
+        assert lo == float(vol.min()) and hi == float(vol.max())
+        width = (hi - lo) / 256
+        for p, want in case["percentiles"].items():
+            got = red.percentile(t, float(p))
+            # same bin as the reference (its float32 histogram and ours agree exactly at these sizes)
+            assert abs(got - want) <= 1e-3 * width + 1e-6 * abs(want), (p, got, want)
+        for bg, want in case["com"].items():
+            got = red.intensity_center_of_mass(t, background=float(bg)).cpu().numpy()
+            assert got.dtype == np.float32
+            # the reference sums in float32; allow its rounding (centroids are O(10-100))
+            assert np.allclose(got, np.array(want), atol=2e-3), (bg, got, want)
+
+
+def test_constant_and_shifted_volumes():
+    import torch
+
+    from shrimpy_b200 import reductions as red
+
+    const = torch.full((5, 6, 7), 3.25, device="cuda")
+    assert red.percentile(const, 50.0) == 3.25                      # vmax <= vmin -> vmin (tracking.py:585-586)
+    assert torch.equal(red.intensity_center_of_mass(const, background=10.0).cpu(), torch.tensor([2.0, 2.5, 3.0]))
+    one = torch.zeros((9, 10, 11), device="cuda")
+    one[4, 7, 2] = 5.0
+    assert torch.equal(red.intensity_center_of_mass(one).cpu(), torch.tensor([4.0, 7.0, 2.0]))
+    neg = -torch.rand((4, 5, 6), device="cuda") - 1.0                # negative "mass" never pulls the centroid
+    assert torch.equal(red.intensity_center_of_mass(neg).cpu(), torch.tensor([1.5, 2.0, 2.5]))
+    with pytest.raises(RuntimeError):
+        red.percentile(torch.zeros(4), 50.0)
+
+
+def test_on_a_deskewed_volume_end_to_end():
+    """deskew -> background percentile -> centre of mass, the chain the tracker runs, vs numpy on the same output."""
+    import torch
+
+    import shrimpy_b200 as sb
+    from helpers import synthetic_stack
+    from shrimpy_b200 import reductions as red
+
+    raw = synthetic_stack((120, 30, 128), seed=2)
+    raw[50:60, 10:14, 40:60] += 5000
+    vol = sb.deskew_zyx(torch.from_numpy(raw).cuda(), 30.0, 0.39, False, 3)
+    host = vol.cpu().numpy().astype(np.float64)
+    bg = red.percentile(vol, 50.0)
+    w = np.clip(host - bg, 0, None)
+    want = [(w.sum(axis=tuple(a for a in range(3) if a != ax)) * np.arange(w.shape[ax])).sum() / w.sum() for ax in range(3)]
+    got = red.intensity_center_of_mass(vol, background=bg).cpu().numpy()
+    assert np.allclose(got, want, rtol=1e-5, atol=1e-4)

@@ -195,3 +195,19 @@ if __name__ == "__main__":
         ff32 = ffm.flat_field_BF(raw)
         res["two_step_ms"] = res["standalone_flatfield_ms"] + timeit(lambda: sb.deskew_zyx(ff32, 30.0, 0.39, False, 3, out=out))
         print(json.dumps({k: round(v, 4) for k, v in res.items()}), flush=True)
+    if "reductions" in args.cases:
+        from shrimpy_b200 import reductions as red
+        vol = torch.rand((100, 2048, 1279), device="cuda") * 1000
+        def t_ms(fn, reps=5):
+            fn(); torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(reps):
+                fn()
+            b.record(); torch.cuda.synchronize()
+            return a.elapsed_time(b) / reps
+        nbytes = vol.numel() * 4
+        r = {"range_ms": t_ms(lambda: red.value_range(vol)), "percentile_ms": t_ms(lambda: red.percentile(vol, 50.0)),
+             "com_ms": t_ms(lambda: red.intensity_center_of_mass(vol, 100.0))}
+        r["range_gbs"] = nbytes / r["range_ms"] / 1e6; r["com_gbs"] = nbytes / r["com_ms"] / 1e6
+        print(json.dumps({k: round(v, 3) for k, v in r.items()}), flush=True)
