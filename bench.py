@@ -197,6 +197,9 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device; shrimpy_b200 has no CPU path")
     torch.cuda.set_device(local)
+    from shrimpy_b200.hostmem import bind_to_gpu
+
+    numa_bound = bind_to_gpu(local) if world > 1 else False     # pinned buffers on the GPU's own NUMA node
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -298,7 +301,7 @@ def run_ours(args):
             "value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": CHANNELS * vox_in * 2,
             "d2h_bytes_per_step": CHANNELS * vox_out * 4, "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps,
             "api": "shrimpy_b200.deskew_data(numpy pinned) -> shrimpy_deskew_host (H2D | kernel | D2H on 3 streams)",
-            "matches_device_path": e2e_ok,
+            "matches_device_path": e2e_ok, "numa_bound": numa_bound,
         },
         "gpu_launches": int(launches),
         "clocks": clocks.summary(),
