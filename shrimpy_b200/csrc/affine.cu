@@ -18,65 +18,13 @@
 //                         nan_to_num is applied lazily: a non-finite result (which every non-finite
 //                         tap produces) is recomputed from cleaned taps.  The host picks the tile
 //                         shape per matrix.
-#include "common.cuh"
+#include "affine_common.cuh"
 
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
 
 namespace shrimpy {
-
-struct AffineParams {
-    const float *in;
-    float *out;
-    int iz, iy, ix;
-    int oz, oy, ox;
-    double M[12];
-    float cval;
-    int nan_to_zero;
-    int tiles_x;  // gather kernel: o2 tiles per row; tile kernel: tiles along o2
-    int tiles_y, tiles_z;
-    int TZ, TY, TX;         // output tile (tile kernel); TY is a power of two
-    int log2TY;
-    int BZ, BY, BX, pitch;  // staged input box and its odd row pitch (tile kernel)
-    unsigned tma_bytes;     // bytes one TMA box load delivers
-    int LA, LB;             // planar kernel: tile extent along the lane axis / the other in-plane axis
-};
-
-constexpr int kAffThreads = 128;
-constexpr int kAffItems = 4;
-constexpr int kTileThreads = 256;
-
-// numpy.nan_to_num: nan -> 0, +-inf -> +-FLT_MAX
-__device__ __forceinline__ float clean(float v) {
-    const uint32_t b = __float_as_uint(v);
-    if ((b & 0x7f800000u) == 0x7f800000u) v = (b & 0x007fffffu) ? 0.f : __uint_as_float(b - 1u);
-    return v;
-}
-
-__device__ __forceinline__ float tap(const float *__restrict__ p, int nan_to_zero) {
-    const float v = __ldg(p);
-    return nan_to_zero ? clean(v) : v;
-}
-
-// One axis of the scipy coordinate: exact float64 value -> (floor, fraction), inside test.
-// c >= 0  <=>  floor >= 0;   c <= dim-1  <=>  floor < dim-1 or (floor == dim-1 and fraction == 0).
-__device__ __forceinline__ bool split_coord(double c, int dim, int &i0, float &w) {
-    i0 = __double2int_rd(c);
-    w = (float)(c - (double)i0);
-    return i0 >= 0 && (i0 < dim - 1 || (i0 == dim - 1 && w == 0.f && c == (double)i0));
-}
-
-// Interior fast path: floor and fraction of a coordinate without 64-bit conversions (F2I.F64,
-// I2F.F64 and F2F.F32.F64 issue at 1/8 rate).  Adding 1.5*2^29 with round-down leaves
-// floor(c * 2^23) + 2^51 in the mantissa: bits [22:0] of the low word are the fraction (23 bits,
-// truncated) and the bits above are floor(c) + 2^28.  Valid for |c| < 2^28 (checked on the host).
-__device__ __forceinline__ int split_fast(double c, float &w) {
-    const double s = __dadd_rd(c, 805306368.0);
-    const unsigned hi = (unsigned)__double2hiint(s), lo = (unsigned)__double2loint(s);
-    w = __uint_as_float((lo & 0x007fffffu) | 0x3f800000u) - 1.0f;
-    return (int)(__funnelshift_l(lo, hi, 9) - 0x90000000u);
-}
 
 __global__ void __launch_bounds__(kAffThreads) affine_gather_kernel(const AffineParams P) {
     const int o1 = blockIdx.x / P.tiles_x;
@@ -620,7 +568,12 @@ extern "C" int shrimpy_affine_device(const float *d_in, float *d_out, int iz, in
                              std::fabs(M[4 * a + 2]) * ox;
         if (!(reach < 134217728.0)) want_gather = true;
     }
-    // Block-diagonal matrix (z <-> z, (y,x) <-> (y,x)): the planar kernel.
+    // Block-diagonal matrix (z <-> z, (y,x) <-> (y,x)): the z-streaming kernel, else the planar tile kernel.
+    if (!want_gather && (!force || force[0] == 's')) {
+        bool launched = false;
+        const int rc = launch_affine_stream(P, nan_to_zero, s, &launched);
+        if (rc != SHRIMPY_OK || launched) return rc;
+    }
     const bool planar_ok = !want_gather && !(force && force[0] != 'p') && M[1] == 0.0 && M[2] == 0.0 && M[4] == 0.0 &&
                            M[8] == 0.0 && (reinterpret_cast<uintptr_t>(d_in) & 15u) == 0 && ix % 4 == 0 &&
                            (long long)oy * ox < 2147483647LL && tensor_map_encoder() != nullptr;

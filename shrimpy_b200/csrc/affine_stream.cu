@@ -1,0 +1,414 @@
+// Z-streaming planar affine resample for sm_100a (registration step, BASELINE.json configs[2]).
+//
+// Block-diagonal matrices (z <-> z, (y,x) <-> (y,x): an in-plane 2-D affine plus a z shift/scale -- the mantis
+// label-free -> fluorescence registration family, and every near-identity map without tilt).
+//
+// One CTA owns an output tile in (o1, o2) and MARCHES through o0.  The input planes the march needs form a
+// monotone sequence z_first, z_first +- 1, ...; a producer warp streams them through a ring of shared-memory
+// slots with one 2-D TMA box per plane (full/empty mbarrier pair per slot), so loads run several planes ahead
+// of the arithmetic and nothing is ever re-read along z.  Eight consumer warps keep, per thread, NC output
+// columns in registers: the exact float64 (y, x) coordinate, floor and weights of a column are computed ONCE
+// for the whole march, the bilinear value of a column in an input plane is computed once per plane and shared
+// by the two output steps that touch it, and the arithmetic is issued as packed float32 pairs
+// (FFMA2 / FADD2, same rounding as the scalar sequence).  Per output step only the z lerp and the store remain.
+//
+// Lanes run along the output axis that walks input x (o2, or o1 for ~90 degree maps: SWAP), so tap reads are
+// conflict-free; with SWAP a step's plane of results is transposed through a double-buffered shared tile so
+// global stores stay coalesced along o2.
+//
+// Exactness: the z coordinate, floor, weight and inside test of a step are tabulated per CTA with scipy's
+// float64 arithmetic; columns within one voxel of the input rim, and non-finite results (nan_to_num), are
+// recomputed by planar_exact_voxel with the exact edge rule.  Interior voxels use the same float32 lerp
+// sequence as every other kernel of this library.
+#include "affine_common.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+
+namespace shrimpy {
+
+constexpr int kStreamConsumerWarps = 8;
+constexpr int kStreamThreads = 32 * (kStreamConsumerWarps + 1);   // + one producer warp
+constexpr int kStreamMaxSteps = 128;
+constexpr int kStreamMaxRing = 8;
+
+struct ZStep {
+    int sA, sB;   // sequence numbers (load order) of the planes holding floor(z) and floor(z)+1
+    float wz;
+    int inside;
+};
+
+__device__ __forceinline__ void consumer_sync() {
+    asm volatile("bar.sync 1, %0;" ::"n"(32 * kStreamConsumerWarps) : "memory");
+}
+
+// Exact voxel of a planar map given its two (already exact) z planes: scipy's (y, x) coordinate arithmetic, the
+// exact edge rule (c == dim-1 is inside, the second tap folds onto the first there), optional nan_to_num of the taps.
+__device__ __noinline__ float planar_exact_voxel(const float *pa, const float *pb, float wz, const AffineParams *Pp,
+                                                 int o1, int o2, int oy0, int ox0, int clean_taps) {
+    const AffineParams &P = *Pp;
+    const double cy = __dadd_rn(__dadd_rn(P.M[7], __dmul_rn((double)o1, P.M[5])), __dmul_rn((double)o2, P.M[6]));
+    const double cx = __dadd_rn(__dadd_rn(P.M[11], __dmul_rn((double)o1, P.M[9])), __dmul_rn((double)o2, P.M[10]));
+    int y0, x0;
+    float wy, wx;
+    bool in = split_coord(cy, P.iy, y0, wy);
+    in &= split_coord(cx, P.ix, x0, wx);
+    if (!in) return P.cval;
+    const int dy = (y0 + 1 < P.iy) ? P.pitch : 0;
+    const int dx = (x0 + 1 < P.ix) ? 1 : 0;
+    const int by = min(max(y0 - oy0, 0), P.BY - 1 - (dy ? 1 : 0));
+    const int bx = min(max(x0 - ox0, 0), P.BX - 1 - dx);
+    const int q = by * P.pitch + bx;
+    float v[8] = {pa[q], pa[q + dx], pa[q + dy], pa[q + dy + dx], pb[q], pb[q + dx], pb[q + dy], pb[q + dy + dx]};
+    if (clean_taps) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = clean(v[i]);
+    }
+    const float a00 = fmaf(wx, v[1] - v[0], v[0]);
+    const float a01 = fmaf(wx, v[3] - v[2], v[2]);
+    const float a10 = fmaf(wx, v[5] - v[4], v[4]);
+    const float a11 = fmaf(wx, v[7] - v[6], v[6]);
+    const float b0 = fmaf(wy, a01 - a00, a00);
+    const float b1 = fmaf(wy, a11 - a10, a10);
+    return fmaf(wz, b1 - b0, b0);
+}
+
+__device__ __forceinline__ float2 neg2(float2 v) { return make_float2(-v.x, -v.y); }
+__device__ __forceinline__ bool nonfinite(float v) { return (__float_as_uint(v) & 0x7f800000u) == 0x7f800000u; }
+
+// IA = items along the lane axis (tile extent 32*IA), RB = rows per warp (tile extent 8*RB along the other axis).
+template <int IA, int RB, bool SWAP, bool CLEAN>
+__global__ void __launch_bounds__(kStreamThreads, (IA * RB <= 4) ? 3 : 2)
+    affine_stream_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ AffineParams P) {
+    constexpr int NC = IA * RB, NC2 = NC / 2;
+    static_assert(NC % 2 == 0 && NC <= 16, "columns are processed in packed pairs");
+    constexpr int LA = 32 * IA, LB = 8 * RB;
+    constexpr int TY = SWAP ? LA : LB, TX = SWAP ? LB : LA;
+    constexpr unsigned ALL = (1u << NC) - 1u;
+
+    extern __shared__ __align__(128) float smem_raw[];
+    __shared__ ZStep ztab[kStreamMaxSteps];
+    __shared__ __align__(8) uint64_t full[kStreamMaxRing], empty[kStreamMaxRing];
+    __shared__ int s_zmin, s_zmax, s_org[2];
+    float *ring = smem_raw + (((128u - (smem_u32(smem_raw) & 127u)) & 127u) >> 2);
+
+    const int ring_log2 = P.ring_log2, mask = (1 << ring_log2) - 1;
+    const int pitch = P.pitch;
+    const int t0y = blockIdx.y * TY, t0x = blockIdx.x * TX, t0z = blockIdx.z * P.ZC;
+    const int nsteps = min(P.ZC, P.oz - t0z);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    // ---- per-CTA set-up: barriers, (y, x) box origin, z table --------------------------------------------------
+    if (tid == 0) {
+        s_zmin = 0x7fffffff;
+        s_zmax = -1;
+        for (int i = 0; i <= mask; ++i) {
+            mbar_init(&full[i], 1);
+            mbar_init(&empty[i], kStreamConsumerWarps);
+        }
+        fence_mbar_init();
+        const double e1 = (double)(min(t0y + TY, P.oy) - 1 - t0y), e2 = (double)(min(t0x + TX, P.ox) - 1 - t0x);
+#pragma unroll
+        for (int a = 1; a < 3; ++a) {
+            const double m1 = P.M[4 * a + 1], m2 = P.M[4 * a + 2];
+            const double lo = P.M[4 * a + 3] + t0y * m1 + t0x * m2 + fmin(e1 * m1, 0.0) + fmin(e2 * m2, 0.0);
+            const int dim = a == 1 ? P.iy : P.ix;
+            int org = __double2int_rd(fmin(fmax(lo - 1e-6, -4.0), (double)dim));
+            if (a == 2) org &= ~3;   // TMA: the box starts on a 16-byte boundary along x
+            s_org[a - 1] = org;
+        }
+    }
+    __syncthreads();
+    int z0 = 0, z1 = 0, inside = 0;
+    float wz = 0.f;
+    if (tid < nsteps) {
+        // ((M03 + o0 M00) + o1*0) + o2*0: scipy's value for every (o1, o2)
+        const double cz = __dadd_rn(P.M[3], __dmul_rn((double)(t0z + tid), P.M[0]));
+        inside = split_coord(cz, P.iz, z0, wz);
+        z1 = min(z0 + 1, P.iz - 1);
+        if (inside) {
+            atomicMin(&s_zmin, z0);
+            atomicMax(&s_zmax, z1);
+        }
+    }
+    __syncthreads();
+    const int zmin = s_zmin, zmax = s_zmax;
+    const bool desc = P.M[0] < 0.0;   // planes are visited downwards
+    if (tid < nsteps) {
+        ZStep e;
+        e.sA = inside ? (desc ? zmax - z0 : z0 - zmin) : 0;
+        e.sB = inside ? (desc ? zmax - z1 : z1 - zmin) : 0;
+        e.wz = wz;
+        e.inside = inside;
+        ztab[tid] = e;
+    }
+    __syncthreads();
+    const int oy0 = s_org[0], ox0 = s_org[1];
+    const unsigned slot_bytes = (unsigned)P.PB * 4u;
+
+    // ---- producer warp: one TMA box per input plane, in march order ----------------------------------------------
+    if (warp == kStreamConsumerWarps) {
+        if (lane == 0) {
+            const int nseq = zmax >= zmin ? zmax - zmin + 1 : 0;
+            const uint32_t ring_s = smem_u32(ring);
+            for (int seq = 0; seq < nseq; ++seq) {
+                const int slot = seq & mask, round = seq >> ring_log2;
+                if (round > 0) mbar_wait(&empty[slot], (round - 1) & 1);
+                mbar_arrive_expect_tx(&full[slot], P.tma_bytes);
+                tma_load_3d(ring_s + slot * slot_bytes, &tmap, ox0, oy0, desc ? zmax - seq : zmin + seq, &full[slot]);
+            }
+        }
+        return;
+    }
+
+    // ---- consumers: per-column set-up (exact (y, x) coordinate, floor, weights, classification) -------------------
+    unsigned qoff[NC];                   // byte offset of the column's first tap inside a plane slot
+    float2 wx2[NC2], wy2[NC2];
+    unsigned fast_mask = 0, out_mask = 0, live_mask = 0;   // bit c: interior column / certainly outside / exists
+    const unsigned hy = (unsigned)max(P.iy - 3, 0), hx = (unsigned)max(P.ix - 3, 0);
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+        const int a = lane + 32 * (c % IA), b = warp + 8 * (c / IA);
+        const int o1 = t0y + (SWAP ? a : b), o2 = t0x + (SWAP ? b : a);
+        float wy = 0.f, wx = 0.f;
+        qoff[c] = 0;
+        if (o1 < P.oy && o2 < P.ox) {
+            live_mask |= 1u << c;
+            const double cy = __dadd_rn(__dadd_rn(P.M[7], __dmul_rn((double)o1, P.M[5])), __dmul_rn((double)o2, P.M[6]));
+            const double cx = __dadd_rn(__dadd_rn(P.M[11], __dmul_rn((double)o1, P.M[9])), __dmul_rn((double)o2, P.M[10]));
+            const int y0 = split_fast(cy, wy), x0 = split_fast(cx, wx);
+            if ((unsigned)(y0 - 1) < hy && (unsigned)(x0 - 1) < hx) {
+                fast_mask |= 1u << c;
+                qoff[c] = (unsigned)((y0 - oy0) * pitch + (x0 - ox0)) * 4u;
+            } else if ((unsigned)(y0 + 1) > (unsigned)P.iy || (unsigned)(x0 + 1) > (unsigned)P.ix) {
+                out_mask |= 1u << c;
+            }
+        }
+        if (c & 1) { wy2[c / 2].y = wy; wx2[c / 2].y = wx; }
+        else       { wy2[c / 2].x = wy; wx2[c / 2].x = wx; }
+    }
+    const unsigned rim_mask = live_mask & ~fast_mask & ~out_mask;   // exact path on every inside step
+    const bool lean = __all_sync(0xffffffffu, live_mask == ALL && fast_mask == ALL);
+
+    const char *ringc = reinterpret_cast<const char *>(ring);
+    auto plane_values = [&](int seq, float2(&dst)[NC2]) {
+        const char *pl = ringc + (unsigned)(seq & mask) * slot_bytes;
+#pragma unroll
+        for (int j = 0; j < NC2; ++j) {
+            const float *q0 = reinterpret_cast<const float *>(pl + qoff[2 * j]);
+            const float *q1 = reinterpret_cast<const float *>(pl + qoff[2 * j + 1]);
+            const float2 lo = make_float2(q0[0], q1[0]), hi = make_float2(q0[1], q1[1]);
+            const float2 lo2 = make_float2(q0[pitch], q1[pitch]), hi2 = make_float2(q0[pitch + 1], q1[pitch + 1]);
+            const float2 a0 = __ffma2_rn(wx2[j], __fadd2_rn(hi, neg2(lo)), lo);
+            const float2 a1 = __ffma2_rn(wx2[j], __fadd2_rn(hi2, neg2(lo2)), lo2);
+            dst[j] = __ffma2_rn(wy2[j], __fadd2_rn(a1, neg2(a0)), a0);
+        }
+    };
+
+    float *otile = ring + ((size_t)P.PB << ring_log2);   // SWAP only: 2 x LA x (LB + 1)
+    const long long plane = (long long)P.oy * P.ox;
+    float *pstep = P.out + (long long)t0z * plane;        // start of output plane t0z (advanced per step)
+    float *pcol = pstep + (long long)(t0y + warp) * P.ox + t0x + lane;   // !SWAP: this thread's column c = 0
+
+    float2 vA[NC2], vB[NC2];
+#pragma unroll
+    for (int j = 0; j < NC2; ++j) vA[j] = vB[j] = make_float2(0.f, 0.f);
+    int hA = -1, hB = -1;          // sequence numbers of the planes whose values sit in vA / vB
+    int ready = 0, released = 0;   // planes [0, ready) have landed; planes [0, released) were handed back
+    const float cval = P.cval;
+
+    for (int lz = 0; lz < nsteps; ++lz, pstep += plane, pcol += plane) {
+        const ZStep e = ztab[lz];
+        float res[NC];
+        unsigned rare = 0;
+        if (e.inside) {
+            const int lo = min(e.sA, e.sB), need = max(e.sA, e.sB) + 1;
+            for (; released < lo; ++released)
+                if (lane == 0) mbar_arrive(&empty[released & mask]);
+            for (; ready < need; ++ready) mbar_wait(&full[ready & mask], (ready >> ring_log2) & 1);
+
+            float2 nA[NC2], nB[NC2];
+            if (e.sA == hA) {
+#pragma unroll
+                for (int j = 0; j < NC2; ++j) nA[j] = vA[j];
+            } else if (e.sA == hB) {
+#pragma unroll
+                for (int j = 0; j < NC2; ++j) nA[j] = vB[j];
+            } else {
+                plane_values(e.sA, nA);
+            }
+            if (e.sB == e.sA) {
+#pragma unroll
+                for (int j = 0; j < NC2; ++j) nB[j] = nA[j];
+            } else if (e.sB == hB) {
+#pragma unroll
+                for (int j = 0; j < NC2; ++j) nB[j] = vB[j];
+            } else if (e.sB == hA) {
+#pragma unroll
+                for (int j = 0; j < NC2; ++j) nB[j] = vA[j];
+            } else {
+                plane_values(e.sB, nB);
+            }
+            hA = e.sA;
+            hB = e.sB;
+            const float2 wz2 = make_float2(e.wz, e.wz);
+            float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int j = 0; j < NC2; ++j) {
+                vA[j] = nA[j];
+                vB[j] = nB[j];
+                const float2 r = __ffma2_rn(wz2, __fadd2_rn(nB[j], neg2(nA[j])), nA[j]);
+                res[2 * j] = r.x;
+                res[2 * j + 1] = r.y;
+                if (CLEAN) acc = __ffma2_rn(r, make_float2(0.f, 0.f), acc);   // stays 0 unless some result is non-finite
+            }
+            if (CLEAN && !(acc.x == 0.f && acc.y == 0.f)) {
+#pragma unroll
+                for (int c = 0; c < NC; ++c)
+                    if (nonfinite(res[c])) rare |= 1u << c;
+                rare &= fast_mask;
+            }
+            if (!lean) {
+#pragma unroll
+                for (int c = 0; c < NC; ++c) res[c] = (fast_mask >> c & 1u) ? res[c] : cval;
+                rare |= rim_mask;
+            }
+        } else {
+#pragma unroll
+            for (int c = 0; c < NC; ++c) res[c] = cval;
+        }
+
+        if (rare) {   // rim columns / non-finite taps: exact recomputation (rare)
+            const float *pa = ring + (size_t)(e.sA & mask) * P.PB, *pb = ring + (size_t)(e.sB & mask) * P.PB;
+#pragma unroll
+            for (int c = 0; c < NC; ++c) {
+                if (rare >> c & 1u) {
+                    const int a = lane + 32 * (c % IA), b = warp + 8 * (c / IA);
+                    res[c] = planar_exact_voxel(pa, pb, e.wz, &P, t0y + (SWAP ? a : b), t0x + (SWAP ? b : a), oy0, ox0, CLEAN);
+                }
+            }
+        }
+
+        if (!SWAP) {
+            if (lean) {
+#pragma unroll
+                for (int rb = 0; rb < RB; ++rb) {
+                    float *prow = pcol + (long long)(8 * rb) * P.ox;
+#pragma unroll
+                    for (int ia = 0; ia < IA; ++ia) __stcs(prow + 32 * ia, res[rb * IA + ia]);
+                }
+            } else {
+#pragma unroll
+                for (int c = 0; c < NC; ++c)
+                    if (live_mask >> c & 1u) __stcs(pcol + (long long)(8 * (c / IA)) * P.ox + 32 * (c % IA), res[c]);
+            }
+        } else {
+            float *ot = otile + (lz & 1) * (LA * (LB + 1));
+#pragma unroll
+            for (int c = 0; c < NC; ++c) ot[(lane + 32 * (c % IA)) * (LB + 1) + warp + 8 * (c / IA)] = res[c];
+            consumer_sync();   // one barrier per step: the other buffer is written while this one drains
+#pragma unroll
+            for (int idx = tid; idx < LA * LB; idx += 32 * kStreamConsumerWarps) {
+                const int a = idx / LB, b = idx % LB;
+                const int o1 = t0y + a, o2 = t0x + b;
+                if (o1 < P.oy && o2 < P.ox) __stcs(pstep + (long long)o1 * P.ox + o2, ot[a * (LB + 1) + b]);
+            }
+        }
+    }
+}
+
+template <int IA, int RB>
+static void (*pick_stream(bool swap, bool clean))(const CUtensorMap, const AffineParams) {
+    return swap ? (clean ? affine_stream_kernel<IA, RB, true, true> : affine_stream_kernel<IA, RB, true, false>)
+                : (clean ? affine_stream_kernel<IA, RB, false, true> : affine_stream_kernel<IA, RB, false, false>);
+}
+
+// Host side: pick the tile, the ring depth and the z chunking, encode the per-plane tensor map, launch.
+// Returns SHRIMPY_OK with *launched = false when the matrix/shape is not eligible (the caller falls back).
+int launch_affine_stream(AffineParams P, int nan_to_zero, cudaStream_t s, bool *launched) {
+    *launched = false;
+    const double *M = P.M;
+    if (!(M[1] == 0.0 && M[2] == 0.0 && M[4] == 0.0 && M[8] == 0.0)) return SHRIMPY_OK;
+    if ((reinterpret_cast<uintptr_t>(P.in) & 15u) != 0 || P.ix % 4 != 0 || (long long)P.oy * P.ox >= 2147483647LL ||
+        tensor_map_encoder() == nullptr)
+        return SHRIMPY_OK;
+    const bool swap = std::fabs(M[9]) > std::fabs(M[10]);   // input x follows o1 more than o2: lanes along o1
+    // (IA, RB): lanes x rows-per-warp.  !swap: tile = (8 RB) x (32 IA) in (o1, o2); swap: (32 IA) x (8 RB), RB >= 4
+    // so that drained rows are >= 128 bytes.
+    static const int cand_plain[][2] = {{4, 2}, {2, 4}, {2, 2}, {4, 1}, {2, 1}};
+    static const int cand_swap[][2] = {{2, 4}, {1, 8}, {1, 4}};
+    int forced[3] = {0, 0, 0};
+    if (const char *f = getenv("SHRIMPY_STREAM_CFG")) sscanf(f, "%d,%d,%d", &forced[0], &forced[1], &forced[2]);
+    double best = 1e300;
+    int bIA = 0, bRB = 0, bring = 0;
+    for (int k = 0; k < (swap ? 3 : 5); ++k) {
+        const int IA = swap ? cand_swap[k][0] : cand_plain[k][0], RB = swap ? cand_swap[k][1] : cand_plain[k][1];
+        if (forced[0] && (IA != forced[0] || RB != forced[1])) continue;
+        const int LA = 32 * IA, LB = 8 * RB, TY = swap ? LA : LB, TX = swap ? LB : LA;
+        const long long BY = (long long)std::ceil(std::fabs(M[5]) * (TY - 1) + std::fabs(M[6]) * (TX - 1)) + 3;
+        long long BX = (long long)std::ceil(std::fabs(M[9]) * (TY - 1) + std::fabs(M[10]) * (TX - 1)) + 3;
+        BX = (BX + 3 + 3) / 4 * 4;
+        if (BY > 256 || BX > 256) continue;
+        const long long PB = (BY * BX + 31) / 32 * 32;
+        const long long otile = swap ? 2LL * LA * (LB + 1) : 0;
+        const int ctas = IA * RB <= 4 ? 3 : 2;
+        const long long budget = (ctas == 3 ? 72 : 110) * 1024;
+        for (int rl = 3; rl >= 2; --rl) {
+            if (forced[2] && (1 << rl) != forced[2]) continue;
+            const long long bytes = ((PB << rl) + otile) * 4 + 128;
+            if (bytes > budget) continue;
+            // cost: staged elements per output voxel; deeper rings and more columns per thread are preferred
+            const double cost = (double)(BY * BX) / (TY * TX) + (rl == 2 ? 0.15 : 0.0) + (IA * RB < 8 ? 0.05 : 0.0);
+            if (cost < best) {
+                best = cost; bIA = IA; bRB = RB; bring = rl;
+                P.BY = (int)BY; P.BX = (int)BX; P.pitch = (int)BX; P.PB = (int)PB; P.BZ = 1;
+                P.LA = LA; P.LB = LB; P.TY = TY; P.TX = TX;
+            }
+            break;
+        }
+    }
+    if (best == 1e300) return SHRIMPY_OK;
+    P.ring_log2 = bring;
+    const int nchunks = (P.oz + kStreamMaxSteps - 1) / kStreamMaxSteps;
+    P.ZC = (P.oz + nchunks - 1) / nchunks;
+    P.tiles_x = (P.ox + P.TX - 1) / P.TX;
+    P.tiles_y = (P.oy + P.TY - 1) / P.TY;
+    P.tiles_z = nchunks;
+    if (P.tiles_y > 65535 || nchunks > 65535) return SHRIMPY_OK;
+
+    CUtensorMap tmap{};
+    const cuuint64_t gdim[3] = {(cuuint64_t)P.ix, (cuuint64_t)P.iy, (cuuint64_t)P.iz};
+    const cuuint64_t gstride[2] = {(cuuint64_t)P.ix * 4, (cuuint64_t)P.ix * P.iy * 4};
+    const cuuint32_t bdim[3] = {(cuuint32_t)P.BX, (cuuint32_t)P.BY, 1u};
+    const cuuint32_t estr[3] = {1u, 1u, 1u};
+    P.tma_bytes = bdim[0] * bdim[1] * 4u;
+    const CUresult rc = tensor_map_encoder()(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(P.in), gdim,
+                                             gstride, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (rc != CUDA_SUCCESS) return fail(SHRIMPY_ECUDA, "affine stream: cuTensorMapEncodeTiled failed (%d)", (int)rc);
+
+    void (*kern)(const CUtensorMap, const AffineParams) = nullptr;
+    const bool cl = nan_to_zero != 0;
+    if (bIA == 4 && bRB == 2) kern = pick_stream<4, 2>(swap, cl);
+    else if (bIA == 2 && bRB == 4) kern = pick_stream<2, 4>(swap, cl);
+    else if (bIA == 2 && bRB == 2) kern = pick_stream<2, 2>(swap, cl);
+    else if (bIA == 4 && bRB == 1) kern = pick_stream<4, 1>(swap, cl);
+    else if (bIA == 2 && bRB == 1) kern = pick_stream<2, 1>(swap, cl);
+    else if (bIA == 1 && bRB == 8) kern = pick_stream<1, 8>(swap, cl);
+    else if (bIA == 1 && bRB == 4) kern = pick_stream<1, 4>(swap, cl);
+    else return SHRIMPY_OK;
+    const size_t smem = (((size_t)P.PB << P.ring_log2) + (swap ? 2 * (size_t)P.LA * (P.LB + 1) : 0)) * sizeof(float) + 128;
+    if (getenv("SHRIMPY_DEBUG"))
+        fprintf(stderr, "[shrimpy] affine stream IA=%d RB=%d swap=%d ring=%d box=(%d,%d) PB=%d ZC=%d smem=%zu grid=(%d,%d,%d)\n",
+                bIA, bRB, (int)swap, 1 << P.ring_log2, P.BY, P.BX, P.PB, P.ZC, smem, P.tiles_x, P.tiles_y, P.tiles_z);
+    if (smem + 4096 > 48 * 1024)
+        SHRIMPY_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<dim3((unsigned)P.tiles_x, (unsigned)P.tiles_y, (unsigned)P.tiles_z), kStreamThreads, smem, s>>>(tmap, P);
+    count_launch();
+    SHRIMPY_CUDA_TRY(cudaGetLastError());
+    *launched = true;
+    return SHRIMPY_OK;
+}
+
+}  // namespace shrimpy
