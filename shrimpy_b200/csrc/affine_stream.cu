@@ -9,17 +9,22 @@
 // of the arithmetic and nothing is ever re-read along z.  Eight consumer warps keep, per thread, NC output
 // columns in registers: the exact float64 (y, x) coordinate, floor and weights of a column are computed ONCE
 // for the whole march, the bilinear value of a column in an input plane is computed once per plane and shared
-// by the two output steps that touch it, and the arithmetic is issued as packed float32 pairs
-// (FFMA2 / FADD2, same rounding as the scalar sequence).  Per output step only the z lerp and the store remain.
+// by the output steps that touch it (two register sets addressed by the parity of the plane's sequence number,
+// so nothing is ever copied), and the arithmetic is issued as packed float32 pairs (FFMA2 / FADD2: half the
+// issue slots, same rounding as the scalar sequence).  Per output step only the z lerp and the store remain.
+//
+// The z coordinate of a step does not depend on (o1, o2): the host tabulates floor, weight, inside test and
+// plane sequence numbers of every step with scipy's float64 arithmetic and passes the table as a kernel
+// parameter, so the per-step bookkeeping (ring waits, reuse tags, branches) runs on the uniform datapath.
 //
 // Lanes run along the output axis that walks input x (o2, or o1 for ~90 degree maps: SWAP), so tap reads are
 // conflict-free; with SWAP a step's plane of results is transposed through a double-buffered shared tile so
 // global stores stay coalesced along o2.
 //
-// Exactness: the z coordinate, floor, weight and inside test of a step are tabulated per CTA with scipy's
-// float64 arithmetic; columns within one voxel of the input rim, and non-finite results (nan_to_num), are
-// recomputed by planar_exact_voxel with the exact edge rule.  Interior voxels use the same float32 lerp
-// sequence as every other kernel of this library.
+// Exactness: every column's (y, x) split uses the exact edge rule (c == dim-1 is inside, its second tap folds
+// onto the first); columns at the rim simply carry zero tap strides.  Non-finite results (nan_to_num semantics)
+// are recomputed from cleaned taps by planar_exact_voxel.  The float32 lerp sequence (x, then y, then z) is the
+// one every kernel of this library uses.
 #include "affine_common.cuh"
 
 #include <algorithm>
@@ -29,7 +34,8 @@
 namespace shrimpy {
 
 constexpr int kStreamConsumerWarps = 8;
-constexpr int kStreamThreads = 32 * (kStreamConsumerWarps + 1);   // + one producer warp
+constexpr int kStreamConsumers = 32 * kStreamConsumerWarps;
+constexpr int kStreamThreads = kStreamConsumers + 32;   // + one producer warp
 constexpr int kStreamMaxSteps = 128;
 constexpr int kStreamMaxRing = 8;
 
@@ -39,12 +45,19 @@ struct ZStep {
     int inside;
 };
 
+struct ZTable {
+    ZStep e[kStreamMaxSteps];
+    int t0z, nsteps;   // output steps [t0z, t0z + nsteps) of this launch
+    int zfirst, zdir;  // plane of sequence number s is zfirst + s * zdir
+    int nseq;
+};
+
 __device__ __forceinline__ void consumer_sync() {
-    asm volatile("bar.sync 1, %0;" ::"n"(32 * kStreamConsumerWarps) : "memory");
+    asm volatile("bar.sync 1, %0;" ::"n"(kStreamConsumers) : "memory");
 }
 
 // Exact voxel of a planar map given its two (already exact) z planes: scipy's (y, x) coordinate arithmetic, the
-// exact edge rule (c == dim-1 is inside, the second tap folds onto the first there), optional nan_to_num of the taps.
+// exact edge rule, nan_to_num of the taps.  Only voxels whose fast result is non-finite come here.
 __device__ __noinline__ float planar_exact_voxel(const float *pa, const float *pb, float wz, const AffineParams *Pp,
                                                  int o1, int o2, int oy0, int ox0, int clean_taps) {
     const AffineParams &P = *Pp;
@@ -57,9 +70,7 @@ __device__ __noinline__ float planar_exact_voxel(const float *pa, const float *p
     if (!in) return P.cval;
     const int dy = (y0 + 1 < P.iy) ? P.pitch : 0;
     const int dx = (x0 + 1 < P.ix) ? 1 : 0;
-    const int by = min(max(y0 - oy0, 0), P.BY - 1 - (dy ? 1 : 0));
-    const int bx = min(max(x0 - ox0, 0), P.BX - 1 - dx);
-    const int q = by * P.pitch + bx;
+    const int q = (y0 - oy0) * P.pitch + (x0 - ox0);
     float v[8] = {pa[q], pa[q + dx], pa[q + dy], pa[q + dy + dx], pb[q], pb[q + dx], pb[q + dy], pb[q + dy + dx]};
     if (clean_taps) {
 #pragma unroll
@@ -75,12 +86,23 @@ __device__ __noinline__ float planar_exact_voxel(const float *pa, const float *p
 }
 
 __device__ __forceinline__ float2 neg2(float2 v) { return make_float2(-v.x, -v.y); }
+__device__ __forceinline__ float2 lerp2(float2 w, float2 a, float2 b) {   // fma(w, b - a, a), per half
+    return __ffma2_rn(w, __fadd2_rn(b, neg2(a)), a);
+}
+// Shared load through a 32-bit shared-window address; volatile keeps it behind the mbarrier wait that precedes it.
+template <int IMM>
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(addr), "n"(IMM));
+    return v;
+}
 __device__ __forceinline__ bool nonfinite(float v) { return (__float_as_uint(v) & 0x7f800000u) == 0x7f800000u; }
 
 // IA = items along the lane axis (tile extent 32*IA), RB = rows per warp (tile extent 8*RB along the other axis).
 template <int IA, int RB, bool SWAP, bool CLEAN>
 __global__ void __launch_bounds__(kStreamThreads, (IA * RB <= 4) ? 3 : 2)
-    affine_stream_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ AffineParams P) {
+    affine_stream_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ AffineParams P,
+                         const __grid_constant__ ZTable T) {
     constexpr int NC = IA * RB, NC2 = NC / 2;
     static_assert(NC % 2 == 0 && NC <= 16, "columns are processed in packed pairs");
     constexpr int LA = 32 * IA, LB = 8 * RB;
@@ -88,75 +110,50 @@ __global__ void __launch_bounds__(kStreamThreads, (IA * RB <= 4) ? 3 : 2)
     constexpr unsigned ALL = (1u << NC) - 1u;
 
     extern __shared__ __align__(128) float smem_raw[];
-    __shared__ ZStep ztab[kStreamMaxSteps];
     __shared__ __align__(8) uint64_t full[kStreamMaxRing], empty[kStreamMaxRing];
-    __shared__ int s_zmin, s_zmax, s_org[2];
     float *ring = smem_raw + (((128u - (smem_u32(smem_raw) & 127u)) & 127u) >> 2);
+    const uint32_t full_s = smem_u32(full), empty_s = smem_u32(empty);
 
     const int ring_log2 = P.ring_log2, mask = (1 << ring_log2) - 1;
     const int pitch = P.pitch;
-    const int t0y = blockIdx.y * TY, t0x = blockIdx.x * TX, t0z = blockIdx.z * P.ZC;
-    const int nsteps = min(P.ZC, P.oz - t0z);
+    const unsigned slot_bytes = (unsigned)P.PB * 4u;
+    const int t0y = blockIdx.y * TY, t0x = blockIdx.x * TX, t0z = T.t0z;
+    const int nsteps = T.nsteps;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
-    // ---- per-CTA set-up: barriers, (y, x) box origin, z table --------------------------------------------------
     if (tid == 0) {
-        s_zmin = 0x7fffffff;
-        s_zmax = -1;
         for (int i = 0; i <= mask; ++i) {
             mbar_init(&full[i], 1);
             mbar_init(&empty[i], kStreamConsumerWarps);
         }
         fence_mbar_init();
+    }
+    // (y, x) origin of the staged box: minimum corner of the tile under the in-plane affine
+    int org[2];
+    {
         const double e1 = (double)(min(t0y + TY, P.oy) - 1 - t0y), e2 = (double)(min(t0x + TX, P.ox) - 1 - t0x);
 #pragma unroll
         for (int a = 1; a < 3; ++a) {
             const double m1 = P.M[4 * a + 1], m2 = P.M[4 * a + 2];
             const double lo = P.M[4 * a + 3] + t0y * m1 + t0x * m2 + fmin(e1 * m1, 0.0) + fmin(e2 * m2, 0.0);
             const int dim = a == 1 ? P.iy : P.ix;
-            int org = __double2int_rd(fmin(fmax(lo - 1e-6, -4.0), (double)dim));
-            if (a == 2) org &= ~3;   // TMA: the box starts on a 16-byte boundary along x
-            s_org[a - 1] = org;
+            org[a - 1] = __double2int_rd(fmin(fmax(lo - 1e-6, -4.0), (double)dim));
         }
+        org[1] &= ~3;   // TMA: the box starts on a 16-byte boundary along x
     }
+    const int oy0 = org[0], ox0 = org[1];
     __syncthreads();
-    int z0 = 0, z1 = 0, inside = 0;
-    float wz = 0.f;
-    if (tid < nsteps) {
-        // ((M03 + o0 M00) + o1*0) + o2*0: scipy's value for every (o1, o2)
-        const double cz = __dadd_rn(P.M[3], __dmul_rn((double)(t0z + tid), P.M[0]));
-        inside = split_coord(cz, P.iz, z0, wz);
-        z1 = min(z0 + 1, P.iz - 1);
-        if (inside) {
-            atomicMin(&s_zmin, z0);
-            atomicMax(&s_zmax, z1);
-        }
-    }
-    __syncthreads();
-    const int zmin = s_zmin, zmax = s_zmax;
-    const bool desc = P.M[0] < 0.0;   // planes are visited downwards
-    if (tid < nsteps) {
-        ZStep e;
-        e.sA = inside ? (desc ? zmax - z0 : z0 - zmin) : 0;
-        e.sB = inside ? (desc ? zmax - z1 : z1 - zmin) : 0;
-        e.wz = wz;
-        e.inside = inside;
-        ztab[tid] = e;
-    }
-    __syncthreads();
-    const int oy0 = s_org[0], ox0 = s_org[1];
-    const unsigned slot_bytes = (unsigned)P.PB * 4u;
 
     // ---- producer warp: one TMA box per input plane, in march order ----------------------------------------------
     if (warp == kStreamConsumerWarps) {
         if (lane == 0) {
-            const int nseq = zmax >= zmin ? zmax - zmin + 1 : 0;
-            const uint32_t ring_s = smem_u32(ring);
-            for (int seq = 0; seq < nseq; ++seq) {
+            const uint32_t ring_s = smem_u32(ring);   // (the consumers keep their own copy)
+            for (int seq = 0; seq < T.nseq; ++seq) {
                 const int slot = seq & mask, round = seq >> ring_log2;
-                if (round > 0) mbar_wait(&empty[slot], (round - 1) & 1);
-                mbar_arrive_expect_tx(&full[slot], P.tma_bytes);
-                tma_load_3d(ring_s + slot * slot_bytes, &tmap, ox0, oy0, desc ? zmax - seq : zmin + seq, &full[slot]);
+                if (round > 0)
+                    while (!mbar_try_wait_s(empty_s + 8u * slot, (round - 1) & 1)) __nanosleep(64);
+                mbar_arrive_expect_tx_s(full_s + 8u * slot, P.tma_bytes);
+                tma_load_3d_s(ring_s + slot * slot_bytes, &tmap, ox0, oy0, T.zfirst + seq * T.zdir, full_s + 8u * slot);
             }
         }
         return;
@@ -165,8 +162,7 @@ __global__ void __launch_bounds__(kStreamThreads, (IA * RB <= 4) ? 3 : 2)
     // ---- consumers: per-column set-up (exact (y, x) coordinate, floor, weights, classification) -------------------
     unsigned qoff[NC];                   // byte offset of the column's first tap inside a plane slot
     float2 wx2[NC2], wy2[NC2];
-    unsigned fast_mask = 0, out_mask = 0, live_mask = 0;   // bit c: interior column / certainly outside / exists
-    const unsigned hy = (unsigned)max(P.iy - 3, 0), hx = (unsigned)max(P.ix - 3, 0);
+    unsigned live = 0, valid = 0, xedge = 0, yedge = 0;   // bit c: column exists / is inside / has no x+1 / no y+1 tap
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
         const int a = lane + 32 * (c % IA), b = warp + 8 * (c / IA);
@@ -174,35 +170,60 @@ __global__ void __launch_bounds__(kStreamThreads, (IA * RB <= 4) ? 3 : 2)
         float wy = 0.f, wx = 0.f;
         qoff[c] = 0;
         if (o1 < P.oy && o2 < P.ox) {
-            live_mask |= 1u << c;
+            live |= 1u << c;
+            // + o0 * 0 contributes exactly +-0, so this is scipy's value for every o0
             const double cy = __dadd_rn(__dadd_rn(P.M[7], __dmul_rn((double)o1, P.M[5])), __dmul_rn((double)o2, P.M[6]));
             const double cx = __dadd_rn(__dadd_rn(P.M[11], __dmul_rn((double)o1, P.M[9])), __dmul_rn((double)o2, P.M[10]));
-            const int y0 = split_fast(cy, wy), x0 = split_fast(cx, wx);
-            if ((unsigned)(y0 - 1) < hy && (unsigned)(x0 - 1) < hx) {
-                fast_mask |= 1u << c;
+            int y0, x0;
+            bool in = split_coord(cy, P.iy, y0, wy);
+            in &= split_coord(cx, P.ix, x0, wx);
+            if (in) {
+                valid |= 1u << c;
+                if (x0 + 1 >= P.ix) xedge |= 1u << c;
+                if (y0 + 1 >= P.iy) yedge |= 1u << c;
                 qoff[c] = (unsigned)((y0 - oy0) * pitch + (x0 - ox0)) * 4u;
-            } else if ((unsigned)(y0 + 1) > (unsigned)P.iy || (unsigned)(x0 + 1) > (unsigned)P.ix) {
-                out_mask |= 1u << c;
             }
         }
         if (c & 1) { wy2[c / 2].y = wy; wx2[c / 2].y = wx; }
         else       { wy2[c / 2].x = wy; wx2[c / 2].x = wx; }
     }
-    const unsigned rim_mask = live_mask & ~fast_mask & ~out_mask;   // exact path on every inside step
-    const bool lean = __all_sync(0xffffffffu, live_mask == ALL && fast_mask == ALL);
+    // lean warp: every column exists, is inside and owns all four taps -> constant tap strides, no predicates
+    const bool lean = __all_sync(0xffffffffu, valid == ALL && xedge == 0 && yedge == 0);
 
-    const char *ringc = reinterpret_cast<const char *>(ring);
-    auto plane_values = [&](int seq, float2(&dst)[NC2]) {
-        const char *pl = ringc + (unsigned)(seq & mask) * slot_bytes;
+    const uint32_t ring_s = smem_u32(ring);
+    const unsigned pitch4 = (unsigned)pitch * 4u;
+    // bilinear value of every column of this thread in the plane with sequence number seq.  Taps are read through
+    // 32-bit shared addresses "uniform plane base + per-column offset (+4)", which fold into the LDS address mode.
+    auto fill = [&](int seq, float2(&dst)[NC2]) {
+        const uint32_t pl = ring_s + (unsigned)(seq & mask) * slot_bytes;
+        if (lean) {
+            const uint32_t pl1 = pl + pitch4;
 #pragma unroll
-        for (int j = 0; j < NC2; ++j) {
-            const float *q0 = reinterpret_cast<const float *>(pl + qoff[2 * j]);
-            const float *q1 = reinterpret_cast<const float *>(pl + qoff[2 * j + 1]);
-            const float2 lo = make_float2(q0[0], q1[0]), hi = make_float2(q0[1], q1[1]);
-            const float2 lo2 = make_float2(q0[pitch], q1[pitch]), hi2 = make_float2(q0[pitch + 1], q1[pitch + 1]);
-            const float2 a0 = __ffma2_rn(wx2[j], __fadd2_rn(hi, neg2(lo)), lo);
-            const float2 a1 = __ffma2_rn(wx2[j], __fadd2_rn(hi2, neg2(lo2)), lo2);
-            dst[j] = __ffma2_rn(wy2[j], __fadd2_rn(a1, neg2(a0)), a0);
+            for (int j = 0; j < NC2; ++j) {
+                const unsigned qa = qoff[2 * j], qb = qoff[2 * j + 1];
+                const float2 lo = make_float2(lds_f32<0>(pl + qa), lds_f32<0>(pl + qb));
+                const float2 hi = make_float2(lds_f32<4>(pl + qa), lds_f32<4>(pl + qb));
+                const float2 lo1 = make_float2(lds_f32<0>(pl1 + qa), lds_f32<0>(pl1 + qb));
+                const float2 hi1 = make_float2(lds_f32<4>(pl1 + qa), lds_f32<4>(pl1 + qb));
+                dst[j] = lerp2(wy2[j], lerp2(wx2[j], lo, hi), lerp2(wx2[j], lo1, hi1));
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < NC2; ++j) {
+                float v[2];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int c = 2 * j + h;
+                    const uint32_t q = pl + qoff[c];
+                    const unsigned dx = (xedge >> c & 1u) ? 0u : 4u, dy = (yedge >> c & 1u) ? 0u : pitch4;
+                    const float v00 = lds_f32<0>(q), v01 = lds_f32<0>(q + dx);
+                    const float v10 = lds_f32<0>(q + dy), v11 = lds_f32<0>(q + dy + dx);
+                    const float wx = h ? wx2[j].y : wx2[j].x, wy = h ? wy2[j].y : wy2[j].x;
+                    const float a0 = fmaf(wx, v01 - v00, v00), a1 = fmaf(wx, v11 - v10, v10);
+                    v[h] = fmaf(wy, a1 - a0, a0);
+                }
+                dst[j] = make_float2(v[0], v[1]);
+            }
         }
     };
 
@@ -211,81 +232,85 @@ __global__ void __launch_bounds__(kStreamThreads, (IA * RB <= 4) ? 3 : 2)
     float *pstep = P.out + (long long)t0z * plane;        // start of output plane t0z (advanced per step)
     float *pcol = pstep + (long long)(t0y + warp) * P.ox + t0x + lane;   // !SWAP: this thread's column c = 0
 
-    float2 vA[NC2], vB[NC2];
+    float2 V0[NC2], V1[NC2];       // plane values: V0 <- planes with even sequence number, V1 <- odd
 #pragma unroll
-    for (int j = 0; j < NC2; ++j) vA[j] = vB[j] = make_float2(0.f, 0.f);
-    int hA = -1, hB = -1;          // sequence numbers of the planes whose values sit in vA / vB
+    for (int j = 0; j < NC2; ++j) V0[j] = V1[j] = make_float2(0.f, 0.f);
+    int tag0 = -1, tag1 = -1;      // sequence numbers held in V0 / V1
     int ready = 0, released = 0;   // planes [0, ready) have landed; planes [0, released) were handed back
     const float cval = P.cval;
+    int outside_steps = 0;
 
     for (int lz = 0; lz < nsteps; ++lz, pstep += plane, pcol += plane) {
-        const ZStep e = ztab[lz];
+        const ZStep e = T.e[lz];
+        if (!e.inside) {   // written by the constant-fill pass below
+            ++outside_steps;
+            if (SWAP) consumer_sync();   // keep the double-buffer cadence of the shared tile
+            continue;
+        }
+        const int lo = min(e.sA, e.sB), hi = max(e.sA, e.sB);
+#pragma unroll 1
+        while (released < lo) {
+            if (lane == 0) mbar_arrive_s(empty_s + 8u * (released & mask));
+            ++released;
+        }
+#pragma unroll 1
+        while (ready <= hi) {
+            mbar_wait_s(full_s + 8u * (ready & mask), (ready >> ring_log2) & 1);
+            ++ready;
+        }
+        // lo and hi (= lo or lo + 1) have different parities: each lives in its own register set
+        const int s_even = (lo & 1) ? hi : lo, s_odd = (lo & 1) ? lo : hi;
+        if (!(s_even & 1) && tag0 != s_even) {
+            fill(s_even, V0);
+            tag0 = s_even;
+        }
+        if ((s_odd & 1) && tag1 != s_odd) {
+            fill(s_odd, V1);
+            tag1 = s_odd;
+        }
         float res[NC];
-        unsigned rare = 0;
-        if (e.inside) {
-            const int lo = min(e.sA, e.sB), need = max(e.sA, e.sB) + 1;
-            for (; released < lo; ++released)
-                if (lane == 0) mbar_arrive(&empty[released & mask]);
-            for (; ready < need; ++ready) mbar_wait(&full[ready & mask], (ready >> ring_log2) & 1);
-
-            float2 nA[NC2], nB[NC2];
-            if (e.sA == hA) {
-#pragma unroll
-                for (int j = 0; j < NC2; ++j) nA[j] = vA[j];
-            } else if (e.sA == hB) {
-#pragma unroll
-                for (int j = 0; j < NC2; ++j) nA[j] = vB[j];
-            } else {
-                plane_values(e.sA, nA);
-            }
-            if (e.sB == e.sA) {
-#pragma unroll
-                for (int j = 0; j < NC2; ++j) nB[j] = nA[j];
-            } else if (e.sB == hB) {
-#pragma unroll
-                for (int j = 0; j < NC2; ++j) nB[j] = vB[j];
-            } else if (e.sB == hA) {
-#pragma unroll
-                for (int j = 0; j < NC2; ++j) nB[j] = vA[j];
-            } else {
-                plane_values(e.sB, nB);
-            }
-            hA = e.sA;
-            hB = e.sB;
+        {
+            float2 r[NC2];
             const float2 wz2 = make_float2(e.wz, e.wz);
-            float2 acc = make_float2(0.f, 0.f);
+            if (e.sA == e.sB) {
+#pragma unroll
+                for (int j = 0; j < NC2; ++j) r[j] = (e.sA & 1) ? V1[j] : V0[j];
+            } else if (e.sA & 1) {
+#pragma unroll
+                for (int j = 0; j < NC2; ++j) r[j] = lerp2(wz2, V1[j], V0[j]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < NC2; ++j) r[j] = lerp2(wz2, V0[j], V1[j]);
+            }
 #pragma unroll
             for (int j = 0; j < NC2; ++j) {
-                vA[j] = nA[j];
-                vB[j] = nB[j];
-                const float2 r = __ffma2_rn(wz2, __fadd2_rn(nB[j], neg2(nA[j])), nA[j]);
-                res[2 * j] = r.x;
-                res[2 * j + 1] = r.y;
-                if (CLEAN) acc = __ffma2_rn(r, make_float2(0.f, 0.f), acc);   // stays 0 unless some result is non-finite
+                res[2 * j] = r[j].x;
+                res[2 * j + 1] = r[j].y;
             }
-            if (CLEAN && !(acc.x == 0.f && acc.y == 0.f)) {
+        }
+        unsigned rare = 0;
+        if (CLEAN) {
+            float2 acc = make_float2(0.f, 0.f);   // stays 0 unless some result is non-finite
+#pragma unroll
+            for (int j = 0; j < NC2; ++j) acc = __ffma2_rn(make_float2(res[2 * j], res[2 * j + 1]), make_float2(0.f, 0.f), acc);
+            if (!(acc.x == 0.f && acc.y == 0.f)) {
 #pragma unroll
                 for (int c = 0; c < NC; ++c)
                     if (nonfinite(res[c])) rare |= 1u << c;
-                rare &= fast_mask;
+                rare &= valid;
             }
-            if (!lean) {
-#pragma unroll
-                for (int c = 0; c < NC; ++c) res[c] = (fast_mask >> c & 1u) ? res[c] : cval;
-                rare |= rim_mask;
-            }
-        } else {
-#pragma unroll
-            for (int c = 0; c < NC; ++c) res[c] = cval;
         }
-
-        if (rare) {   // rim columns / non-finite taps: exact recomputation (rare)
+        if (!lean) {
+#pragma unroll
+            for (int c = 0; c < NC; ++c) res[c] = (valid >> c & 1u) ? res[c] : cval;
+        }
+        if (rare) {   // non-finite taps: exact recomputation from cleaned taps (rare)
             const float *pa = ring + (size_t)(e.sA & mask) * P.PB, *pb = ring + (size_t)(e.sB & mask) * P.PB;
 #pragma unroll
             for (int c = 0; c < NC; ++c) {
                 if (rare >> c & 1u) {
                     const int a = lane + 32 * (c % IA), b = warp + 8 * (c / IA);
-                    res[c] = planar_exact_voxel(pa, pb, e.wz, &P, t0y + (SWAP ? a : b), t0x + (SWAP ? b : a), oy0, ox0, CLEAN);
+                    res[c] = planar_exact_voxel(pa, pb, e.wz, &P, t0y + (SWAP ? a : b), t0x + (SWAP ? b : a), oy0, ox0, 1);
                 }
             }
         }
@@ -301,7 +326,7 @@ __global__ void __launch_bounds__(kStreamThreads, (IA * RB <= 4) ? 3 : 2)
             } else {
 #pragma unroll
                 for (int c = 0; c < NC; ++c)
-                    if (live_mask >> c & 1u) __stcs(pcol + (long long)(8 * (c / IA)) * P.ox + 32 * (c % IA), res[c]);
+                    if (live >> c & 1u) __stcs(pcol + (long long)(8 * (c / IA)) * P.ox + 32 * (c % IA), res[c]);
             }
         } else {
             float *ot = otile + (lz & 1) * (LA * (LB + 1));
@@ -309,23 +334,71 @@ __global__ void __launch_bounds__(kStreamThreads, (IA * RB <= 4) ? 3 : 2)
             for (int c = 0; c < NC; ++c) ot[(lane + 32 * (c % IA)) * (LB + 1) + warp + 8 * (c / IA)] = res[c];
             consumer_sync();   // one barrier per step: the other buffer is written while this one drains
 #pragma unroll
-            for (int idx = tid; idx < LA * LB; idx += 32 * kStreamConsumerWarps) {
+            for (int idx = tid; idx < LA * LB; idx += kStreamConsumers) {
                 const int a = idx / LB, b = idx % LB;
                 const int o1 = t0y + a, o2 = t0x + b;
                 if (o1 < P.oy && o2 < P.ox) __stcs(pstep + (long long)o1 * P.ox + o2, ot[a * (LB + 1) + b]);
             }
         }
     }
+
+    // ---- steps whose z lies outside the input: constant fill, rows along o2 -----------------------------------------
+    if (outside_steps) {
+        for (int lz = 0; lz < nsteps; ++lz) {
+            if (T.e[lz].inside) continue;
+            float *pz = P.out + (long long)(t0z + lz) * plane;
+            for (int idx = tid; idx < TY * TX; idx += kStreamConsumers) {
+                const int o1 = t0y + idx / TX, o2 = t0x + idx % TX;
+                if (o1 < P.oy && o2 < P.ox) __stcs(pz + (long long)o1 * P.ox + o2, cval);
+            }
+        }
+    }
 }
 
 template <int IA, int RB>
-static void (*pick_stream(bool swap, bool clean))(const CUtensorMap, const AffineParams) {
+static void (*pick_stream(bool swap, bool clean))(const CUtensorMap, const AffineParams, const ZTable) {
     return swap ? (clean ? affine_stream_kernel<IA, RB, true, true> : affine_stream_kernel<IA, RB, true, false>)
                 : (clean ? affine_stream_kernel<IA, RB, false, true> : affine_stream_kernel<IA, RB, false, false>);
 }
 
-// Host side: pick the tile, the ring depth and the z chunking, encode the per-plane tensor map, launch.
-// Returns SHRIMPY_OK with *launched = false when the matrix/shape is not eligible (the caller falls back).
+// z table of output steps [t0z, t0z + nsteps): scipy's coordinate ((M03 + o0 M00) + o1*0) + o2*0 in float64,
+// exact floor / weight / edge rule (the host twin of split_coord), planes numbered in march order.
+static void build_ztable(const AffineParams &P, int t0z, int nsteps, ZTable &T) {
+    int z0[kStreamMaxSteps], z1[kStreamMaxSteps];
+    int zmin = 0x7fffffff, zmax = -1;
+    T.t0z = t0z;
+    T.nsteps = nsteps;
+    for (int k = 0; k < nsteps; ++k) {
+        volatile double prod = (double)(t0z + k) * P.M[0];   // product and sum rounded separately
+        const double cz = P.M[3] + prod;
+        ZStep &e = T.e[k];
+        e.sA = e.sB = 0;
+        e.wz = 0.f;
+        e.inside = 0;
+        if (!(cz >= 0.0) || !(cz <= (double)(P.iz - 1))) continue;   // scipy: strict outside test, no tolerance
+        const int f = (int)std::floor(cz);
+        const float w = (float)(cz - (double)f);
+        if (!(f < P.iz - 1 || (f == P.iz - 1 && w == 0.f && cz == (double)f))) continue;
+        z0[k] = f;
+        z1[k] = std::min(f + 1, P.iz - 1);
+        e.wz = w;
+        e.inside = 1;
+        zmin = std::min(zmin, z0[k]);
+        zmax = std::max(zmax, z1[k]);
+    }
+    const bool desc = P.M[0] < 0.0;
+    T.zdir = desc ? -1 : 1;
+    T.nseq = zmax >= zmin ? zmax - zmin + 1 : 0;
+    T.zfirst = T.nseq ? (desc ? zmax : zmin) : 0;
+    for (int k = 0; k < nsteps; ++k) {
+        if (!T.e[k].inside) continue;
+        T.e[k].sA = desc ? zmax - z0[k] : z0[k] - zmin;
+        T.e[k].sB = desc ? zmax - z1[k] : z1[k] - zmin;
+    }
+}
+
+// Host side: pick the tile and the ring depth, encode the per-plane tensor map, launch one grid per chunk of
+// <= 128 output steps.  Returns SHRIMPY_OK with *launched = false when the matrix/shape is not eligible.
 int launch_affine_stream(AffineParams P, int nan_to_zero, cudaStream_t s, bool *launched) {
     *launched = false;
     const double *M = P.M;
@@ -375,7 +448,7 @@ int launch_affine_stream(AffineParams P, int nan_to_zero, cudaStream_t s, bool *
     P.tiles_x = (P.ox + P.TX - 1) / P.TX;
     P.tiles_y = (P.oy + P.TY - 1) / P.TY;
     P.tiles_z = nchunks;
-    if (P.tiles_y > 65535 || nchunks > 65535) return SHRIMPY_OK;
+    if (P.tiles_y > 65535) return SHRIMPY_OK;
 
     CUtensorMap tmap{};
     const cuuint64_t gdim[3] = {(cuuint64_t)P.ix, (cuuint64_t)P.iy, (cuuint64_t)P.iz};
@@ -388,7 +461,7 @@ int launch_affine_stream(AffineParams P, int nan_to_zero, cudaStream_t s, bool *
                                              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (rc != CUDA_SUCCESS) return fail(SHRIMPY_ECUDA, "affine stream: cuTensorMapEncodeTiled failed (%d)", (int)rc);
 
-    void (*kern)(const CUtensorMap, const AffineParams) = nullptr;
+    void (*kern)(const CUtensorMap, const AffineParams, const ZTable) = nullptr;
     const bool cl = nan_to_zero != 0;
     if (bIA == 4 && bRB == 2) kern = pick_stream<4, 2>(swap, cl);
     else if (bIA == 2 && bRB == 4) kern = pick_stream<2, 4>(swap, cl);
@@ -400,12 +473,17 @@ int launch_affine_stream(AffineParams P, int nan_to_zero, cudaStream_t s, bool *
     else return SHRIMPY_OK;
     const size_t smem = (((size_t)P.PB << P.ring_log2) + (swap ? 2 * (size_t)P.LA * (P.LB + 1) : 0)) * sizeof(float) + 128;
     if (getenv("SHRIMPY_DEBUG"))
-        fprintf(stderr, "[shrimpy] affine stream IA=%d RB=%d swap=%d ring=%d box=(%d,%d) PB=%d ZC=%d smem=%zu grid=(%d,%d,%d)\n",
-                bIA, bRB, (int)swap, 1 << P.ring_log2, P.BY, P.BX, P.PB, P.ZC, smem, P.tiles_x, P.tiles_y, P.tiles_z);
+        fprintf(stderr, "[shrimpy] affine stream IA=%d RB=%d swap=%d ring=%d box=(%d,%d) PB=%d ZC=%d smem=%zu grid=(%d,%d) x %d launches\n",
+                bIA, bRB, (int)swap, 1 << P.ring_log2, P.BY, P.BX, P.PB, P.ZC, smem, P.tiles_x, P.tiles_y, nchunks);
     if (smem + 4096 > 48 * 1024)
         SHRIMPY_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<dim3((unsigned)P.tiles_x, (unsigned)P.tiles_y, (unsigned)P.tiles_z), kStreamThreads, smem, s>>>(tmap, P);
-    count_launch();
+    for (int ch = 0; ch < nchunks; ++ch) {
+        ZTable T;
+        const int t0z = ch * P.ZC;
+        build_ztable(P, t0z, std::min(P.ZC, P.oz - t0z), T);
+        kern<<<dim3((unsigned)P.tiles_x, (unsigned)P.tiles_y), kStreamThreads, smem, s>>>(tmap, P, T);
+        count_launch();
+    }
     SHRIMPY_CUDA_TRY(cudaGetLastError());
     *launched = true;
     return SHRIMPY_OK;

@@ -84,6 +84,43 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         : "memory");
 }
 
+// The same primitives on 32-bit shared-window addresses (no generic -> shared conversion in hot loops).
+__device__ __forceinline__ void mbar_arrive_s(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive_expect_tx_s(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ bool mbar_try_wait_s(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+
+__device__ __forceinline__ void mbar_wait_s(uint32_t bar, uint32_t parity) {
+    while (!mbar_try_wait_s(bar, parity)) {
+    }
+}
+
+__device__ __forceinline__ void tma_load_3d_s(uint32_t smem_dst, const CUtensorMap *tmap, int c0, int c1, int c2,
+                                              uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+        "[%0], [%1, {%2, %3, %4}], [%5];" ::"r"(smem_dst),
+        "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
+        : "memory");
+}
+
 // One 3-D TMA box load, global -> shared, completion signalled on an mbarrier.
 __device__ __forceinline__ void tma_load_3d(uint32_t smem_dst, const CUtensorMap *tmap, int c0, int c1, int c2,
                                             uint64_t *bar) {
