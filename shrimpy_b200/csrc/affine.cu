@@ -573,6 +573,14 @@ extern "C" int shrimpy_affine_device(const float *d_in, float *d_out, int iz, in
         bool launched = false;
         const int rc = launch_affine_stream(P, nan_to_zero, s, &launched);
         if (rc != SHRIMPY_OK || launched) return rc;
+        if (force && force[1] == '!') return fail(SHRIMPY_EINVAL, "affine: the stream kernel was forced but is not eligible");
+    }
+    // General matrix with a small z spread per tile (rotations of a few degrees): the marching tilt kernel.
+    if (!want_gather && (!force || force[0] == 'm')) {
+        bool launched = false;
+        const int rc = launch_affine_tilt(P, nan_to_zero, s, &launched);
+        if (rc != SHRIMPY_OK || launched) return rc;
+        if (force && force[1] == '!') return fail(SHRIMPY_EINVAL, "affine: the tilt kernel was forced but is not eligible");
     }
     const bool planar_ok = !want_gather && !(force && force[0] != 'p') && M[1] == 0.0 && M[2] == 0.0 && M[4] == 0.0 &&
                            M[8] == 0.0 && (reinterpret_cast<uintptr_t>(d_in) & 15u) == 0 && ix % 4 == 0 &&

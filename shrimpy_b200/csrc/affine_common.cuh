@@ -58,6 +58,23 @@ __device__ __forceinline__ int split_fast(double c, float &w) {
     return (int)(__funnelshift_l(lo, hi, 9) - 0x90000000u);
 }
 
+// ---- packed float32 pairs (FFMA2 / FADD2 on sm_100: half the issue slots of the scalar sequence, same rounding) ----
+__device__ __forceinline__ float2 neg2(float2 v) { return make_float2(-v.x, -v.y); }
+__device__ __forceinline__ float2 lerp2(float2 w, float2 a, float2 b) {   // fma(w, b - a, a), per half
+    return __ffma2_rn(w, __fadd2_rn(b, neg2(a)), a);
+}
+// Shared load through a 32-bit shared-window address; volatile keeps it behind the mbarrier wait that precedes it.
+template <int IMM>
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(addr), "n"(IMM));
+    return v;
+}
+__device__ __forceinline__ bool nonfinite(float v) { return (__float_as_uint(v) & 0x7f800000u) == 0x7f800000u; }
+
+// affine_tilt.cu: z-streaming kernel for general matrices with a small z spread per tile.
+int launch_affine_tilt(AffineParams P, int nan_to_zero, cudaStream_t s, bool *launched);
+
 // affine_stream.cu: z-streaming kernel for block-diagonal matrices.  *launched = false when not eligible.
 int launch_affine_stream(AffineParams P, int nan_to_zero, cudaStream_t s, bool *launched);
 

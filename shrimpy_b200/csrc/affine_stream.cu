@@ -85,19 +85,6 @@ __device__ __noinline__ float planar_exact_voxel(const float *pa, const float *p
     return fmaf(wz, b1 - b0, b0);
 }
 
-__device__ __forceinline__ float2 neg2(float2 v) { return make_float2(-v.x, -v.y); }
-__device__ __forceinline__ float2 lerp2(float2 w, float2 a, float2 b) {   // fma(w, b - a, a), per half
-    return __ffma2_rn(w, __fadd2_rn(b, neg2(a)), a);
-}
-// Shared load through a 32-bit shared-window address; volatile keeps it behind the mbarrier wait that precedes it.
-template <int IMM>
-__device__ __forceinline__ float lds_f32(uint32_t addr) {
-    float v;
-    asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(addr), "n"(IMM));
-    return v;
-}
-__device__ __forceinline__ bool nonfinite(float v) { return (__float_as_uint(v) & 0x7f800000u) == 0x7f800000u; }
-
 // IA = items along the lane axis (tile extent 32*IA), RB = rows per warp (tile extent 8*RB along the other axis).
 template <int IA, int RB, bool SWAP, bool CLEAN>
 __global__ void __launch_bounds__(kStreamThreads, (IA * RB <= 4) ? 3 : 2)

@@ -1,0 +1,421 @@
+// Z-streaming affine resample for GENERAL matrices with a small z spread per tile (registration step,
+// BASELINE.json configs[2]: rotations of a few degrees about every axis, anisotropic scale, translation).
+//
+// Same machine as affine_stream.cu -- one CTA owns an output tile in (o1, o2) and marches through o0 while a
+// producer warp streams input planes through a shared-memory ring with one 2-D TMA box per plane -- but here the
+// z coordinate of a voxel depends on (o1, o2) too, so
+//   * a step needs a WINDOW of planes [floor(min cz), floor(max cz) + 1] over the tile; the window slides
+//     monotonically with o0, plane z lives in slot (z - 1) & (R - 1), and the per-step wait / release counts
+//     are tabulated per CTA in shared memory (float64 corner arithmetic, margins of 1e-6);
+//   * the (y, x) footprint of the tile drifts with o0; the staged box covers the whole march of the launch
+//     (the host bounds the march length so that it fits);
+//   * all three coordinates advance per step in 32.32 fixed point (two integer adds per axis: the floor is the
+//     high word for free, the lerp weight is the low word).  The start value of a column is scipy's exact
+//     float64 coordinate; after <= 128 steps the drift is < 2e-8 voxel, harmless for a voxel at least one
+//     input voxel away from the rim of the input (the interpolant is continuous).  Every other voxel (rim
+//     shell, non-finite result) is recomputed from the output index with scipy's exact arithmetic and edge
+//     rule (tilt_exact_voxel); voxels with floor <= -2 or >= dim on some axis are certainly outside.
+// Interior arithmetic is issued as packed float32 pairs over two columns of a thread (FFMA2 / FADD2).
+#include "affine_common.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+
+namespace shrimpy {
+
+constexpr int kTiltConsumerWarps = 8;
+constexpr int kTiltConsumers = 32 * kTiltConsumerWarps;
+constexpr int kTiltThreads = kTiltConsumers + 32;   // + one producer warp
+constexpr int kTiltMaxSteps = 128;
+constexpr int kTiltMaxRing = 16;
+
+struct TiltParams {
+    long long step_fix[3];   // per-o0 coordinate increments (z, y, x), 32.32 fixed point
+    int t0z, nsteps;         // output steps [t0z, t0z + nsteps) of this launch
+    int dir;                 // +1: planes are visited upwards, -1: downwards
+    int pad;
+};
+
+__device__ __forceinline__ float frac_weight(unsigned lo) {   // low word of a 32.32 coordinate -> [0, 1), 23 bits
+    return __uint_as_float((lo >> 9) | 0x3f800000u) - 1.0f;
+}
+
+// Exact voxel: scipy's coordinate arithmetic from the output index, exact edge rule, clamped taps, nan_to_num.
+__device__ __noinline__ float tilt_exact_voxel(const float *ring, const AffineParams *Pp, int o0, int o1, int o2, int oy0,
+                                               int ox0, int clean_taps) {
+    const AffineParams &P = *Pp;
+    double c[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        double t = __dadd_rn(P.M[4 * a + 3], __dmul_rn((double)o0, P.M[4 * a + 0]));
+        t = __dadd_rn(t, __dmul_rn((double)o1, P.M[4 * a + 1]));
+        c[a] = __dadd_rn(t, __dmul_rn((double)o2, P.M[4 * a + 2]));
+    }
+    int z0, y0, x0;
+    float wz, wy, wx;
+    bool in = split_coord(c[0], P.iz, z0, wz);
+    in &= split_coord(c[1], P.iy, y0, wy);
+    in &= split_coord(c[2], P.ix, x0, wx);
+    if (!in) return P.cval;
+    const int mask = (1 << P.ring_log2) - 1;
+    const int z1 = min(z0 + 1, P.iz - 1);
+    const float *pa = ring + (size_t)((z0 - 1) & mask) * P.PB, *pb = ring + (size_t)((z1 - 1) & mask) * P.PB;
+    const int dy = (y0 + 1 < P.iy) ? P.pitch : 0;
+    const int dx = (x0 + 1 < P.ix) ? 1 : 0;
+    const int q = min(max(y0 - oy0, 0), P.BY - 2) * P.pitch + min(max(x0 - ox0, 0), P.BX - 2);
+    float v[8] = {pa[q], pa[q + dx], pa[q + dy], pa[q + dy + dx], pb[q], pb[q + dx], pb[q + dy], pb[q + dy + dx]};
+    if (clean_taps) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = clean(v[i]);
+    }
+    const float a00 = fmaf(wx, v[1] - v[0], v[0]);
+    const float a01 = fmaf(wx, v[3] - v[2], v[2]);
+    const float a10 = fmaf(wx, v[5] - v[4], v[4]);
+    const float a11 = fmaf(wx, v[7] - v[6], v[6]);
+    const float b0 = fmaf(wy, a01 - a00, a00);
+    const float b1 = fmaf(wy, a11 - a10, a10);
+    return fmaf(wz, b1 - b0, b0);
+}
+
+// IA = items along o2 per lane (tile extent 32*IA), RB = rows per warp (tile extent 8*RB along o1).
+template <int IA, int RB, bool CLEAN>
+__global__ void __launch_bounds__(kTiltThreads, (IA * RB <= 4) ? 3 : 2)
+    affine_tilt_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ AffineParams P,
+                       const __grid_constant__ TiltParams Q) {
+    constexpr int NC = IA * RB, NC2 = NC / 2;
+    static_assert(NC % 2 == 0 && NC <= 8, "columns are processed in packed pairs");
+    constexpr int TY = 8 * RB, TX = 32 * IA;
+
+    extern __shared__ __align__(128) float smem_raw[];
+    __shared__ __align__(8) uint64_t full[kTiltMaxRing], empty[kTiltMaxRing];
+    __shared__ int2 win[kTiltMaxSteps];   // per step: planes [0, x) must have landed, planes [0, y) may be handed back
+    __shared__ int s_zmin, s_zmax;
+    float *ring = smem_raw + (((128u - (smem_u32(smem_raw) & 127u)) & 127u) >> 2);
+    const uint32_t full_s = smem_u32(full), empty_s = smem_u32(empty), ring_s = smem_u32(ring);
+
+    const int ring_log2 = P.ring_log2, mask = (1 << ring_log2) - 1;
+    const int pitch = P.pitch;
+    const unsigned slot_bytes = (unsigned)P.PB * 4u, pitch4 = (unsigned)pitch * 4u;
+    const int t0y = blockIdx.y * TY, t0x = blockIdx.x * TX, t0z = Q.t0z;
+    const int nsteps = Q.nsteps, dir = Q.dir;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    if (tid == 0) {
+        s_zmin = 0x7fffffff;
+        s_zmax = -0x7fffffff;
+        for (int i = 0; i <= mask; ++i) {
+            mbar_init(&full[i], 1);
+            mbar_init(&empty[i], kTiltConsumerWarps);
+        }
+        fence_mbar_init();
+    }
+    // extents of the (clipped) tile and of the march, as float64 offsets from the tile's first voxel
+    const double e0 = (double)(nsteps - 1);
+    const double e1 = (double)(min(t0y + TY, P.oy) - 1 - t0y), e2 = (double)(min(t0x + TX, P.ox) - 1 - t0x);
+    // (y, x) origin of the staged box: minimum corner of tile x march under the affine map
+    int org[2];
+#pragma unroll
+    for (int a = 1; a < 3; ++a) {
+        const double m0 = P.M[4 * a], m1 = P.M[4 * a + 1], m2 = P.M[4 * a + 2];
+        const double lo = P.M[4 * a + 3] + t0z * m0 + t0y * m1 + t0x * m2 + fmin(e0 * m0, 0.0) + fmin(e1 * m1, 0.0) +
+                          fmin(e2 * m2, 0.0);
+        const int dim = a == 1 ? P.iy : P.ix;
+        org[a - 1] = __double2int_rd(fmin(fmax(lo - 1e-6, -4.0), (double)dim));
+    }
+    org[1] &= ~3;   // TMA: the box starts on a 16-byte boundary along x
+    const int oy0 = org[0], ox0 = org[1];
+    __syncthreads();
+
+    // ---- per-step plane window of this tile -----------------------------------------------------------------------
+    int lo_k = 0, hi_k = 0, any = 0;
+    if (tid < nsteps) {
+        const double base = P.M[3] + (double)(t0z + tid) * P.M[0] + t0y * P.M[1] + t0x * P.M[2];
+        const double cmin = base + fmin(e1 * P.M[1], 0.0) + fmin(e2 * P.M[2], 0.0);
+        const double cmax = base + fmax(e1 * P.M[1], 0.0) + fmax(e2 * P.M[2], 0.0);
+        const int zlo = __double2int_rd(fmin(fmax(cmin - 1e-6, -1e9), 1e9));
+        const int zhi = __double2int_rd(fmin(fmax(cmax + 1e-6, -1e9), 1e9)) + 1;
+        any = zhi >= 0 && zlo <= P.iz - 1;
+        lo_k = min(max(zlo, 0), P.iz - 1);
+        hi_k = min(max(zhi, 0), P.iz - 1);
+        if (any) {
+            atomicMin(&s_zmin, lo_k);
+            atomicMax(&s_zmax, hi_k);
+        }
+    }
+    __syncthreads();
+    const int zmin = s_zmin, zmax = s_zmax;
+    const int nseq = zmax >= zmin ? zmax - zmin + 1 : 0;
+    const int zstart = dir >= 0 ? zmin : zmax;   // plane of sequence number s is zstart + dir * s
+    if (tid < nsteps) {
+        int2 w = make_int2(0, 0);
+        if (any) w = dir >= 0 ? make_int2(hi_k - zmin + 1, lo_k - zmin) : make_int2(zmax - lo_k + 1, zmax - hi_k);
+        win[tid] = w;
+    }
+    __syncthreads();
+
+    // ---- producer warp: one TMA box per input plane, in march order ---------------------------------------------------
+    if (warp == kTiltConsumerWarps) {
+        if (lane == 0) {
+            for (int seq = 0; seq < nseq; ++seq) {
+                const int z = zstart + dir * seq;
+                const unsigned slot = (unsigned)(z - 1) & mask;
+                const int round = seq >> ring_log2;
+                if (round > 0)
+                    while (!mbar_try_wait_s(empty_s + 8u * slot, (round - 1) & 1)) __nanosleep(64);
+                mbar_arrive_expect_tx_s(full_s + 8u * slot, P.tma_bytes);
+                tma_load_3d_s(ring_s + slot * slot_bytes, &tmap, ox0, oy0, z, full_s + 8u * slot);
+            }
+        }
+        return;
+    }
+
+    // ---- consumers: column start coordinates (scipy's exact float64 value at o0 = t0z, minus one, 32.32 fixed point) ----
+    long long zf[NC], yf[NC], xf[NC];
+    unsigned live = 0;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+        const int o1 = t0y + warp + 8 * (c / IA), o2 = t0x + lane + 32 * (c % IA);
+        double cc[3];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            double t = __dadd_rn(P.M[4 * a + 3], __dmul_rn((double)t0z, P.M[4 * a + 0]));
+            t = __dadd_rn(t, __dmul_rn((double)o1, P.M[4 * a + 1]));
+            cc[a] = __dadd_rn(t, __dmul_rn((double)o2, P.M[4 * a + 2]));
+        }
+        if (o1 < P.oy && o2 < P.ox) live |= 1u << c;
+        zf[c] = __double2ll_rd((cc[0] - 1.0) * 4294967296.0);
+        yf[c] = __double2ll_rd((cc[1] - 1.0) * 4294967296.0);
+        xf[c] = __double2ll_rd((cc[2] - 1.0) * 4294967296.0);
+    }
+    const long long dzf = Q.step_fix[0], dyf = Q.step_fix[1], dxf = Q.step_fix[2];
+    // high words hold floor(c) - 1: interior (both taps exist, nothing to clamp) <=> 0 <= floor - 1 <= dim - 4
+    const unsigned hz = (unsigned)max(P.iz - 3, 0), hy = (unsigned)max(P.iy - 3, 0), hx = (unsigned)max(P.ix - 3, 0);
+    const unsigned uz = (unsigned)P.iz, uy = (unsigned)P.iy, ux = (unsigned)P.ix;
+    // tap address = ring + slot * slot_bytes + ((y0 - oy0) * pitch + (x0 - ox0)) * 4, with y0 = ym + 1, x0 = xm + 1
+    const uint32_t base0 = ring_s + (unsigned)((1 - oy0) * pitch + (1 - ox0)) * 4u, base1 = base0 + pitch4;
+
+    const long long plane = (long long)P.oy * P.ox;
+    float *pcol = P.out + (long long)t0z * plane + (long long)(t0y + warp) * P.ox + t0x + lane;   // column c = 0
+    const float cval = P.cval;
+    int ready = 0, released = 0;   // planes [0, ready) have landed; planes [0, released) were handed back
+
+    for (int lz = 0; lz < nsteps; ++lz, pcol += plane) {
+        const int2 w = win[lz];
+#pragma unroll 1
+        while (released < w.y) {
+            if (lane == 0) mbar_arrive_s(empty_s + 8u * ((unsigned)(zstart + dir * released - 1) & mask));
+            ++released;
+        }
+#pragma unroll 1
+        while (ready < w.x) {
+            mbar_wait_s(full_s + 8u * ((unsigned)(zstart + dir * ready - 1) & mask), (ready >> ring_log2) & 1);
+            ++ready;
+        }
+
+        // classification of this step's voxels
+        bool fast_all = true;
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+            const unsigned zm = (unsigned)(zf[c] >> 32), ym = (unsigned)(yf[c] >> 32), xm = (unsigned)(xf[c] >> 32);
+            fast_all = fast_all && zm < hz && ym < hy && xm < hx;
+        }
+        fast_all = __all_sync(0xffffffffu, fast_all && live == (1u << NC) - 1u);
+
+        float res[NC];
+        if (fast_all) {
+#pragma unroll
+            for (int j = 0; j < NC2; ++j) {
+                unsigned offA[2], offB[2];
+                float wz[2], wy[2], wx[2];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int c = 2 * j + h;
+                    const int zm = (int)(zf[c] >> 32), ym = (int)(yf[c] >> 32), xm = (int)(xf[c] >> 32);
+                    wz[h] = frac_weight((unsigned)zf[c]);
+                    wy[h] = frac_weight((unsigned)yf[c]);
+                    wx[h] = frac_weight((unsigned)xf[c]);
+                    const unsigned inpl = (unsigned)ym * pitch4 + ((unsigned)xm << 2);
+                    offA[h] = ((unsigned)zm & mask) * slot_bytes + inpl;
+                    offB[h] = ((unsigned)(zm + 1) & mask) * slot_bytes + inpl;
+                }
+                const float2 wx2 = make_float2(wx[0], wx[1]), wy2 = make_float2(wy[0], wy[1]), wz2 = make_float2(wz[0], wz[1]);
+                const float2 a00 = make_float2(lds_f32<0>(base0 + offA[0]), lds_f32<0>(base0 + offA[1]));
+                const float2 a01 = make_float2(lds_f32<4>(base0 + offA[0]), lds_f32<4>(base0 + offA[1]));
+                const float2 a10 = make_float2(lds_f32<0>(base1 + offA[0]), lds_f32<0>(base1 + offA[1]));
+                const float2 a11 = make_float2(lds_f32<4>(base1 + offA[0]), lds_f32<4>(base1 + offA[1]));
+                const float2 b00 = make_float2(lds_f32<0>(base0 + offB[0]), lds_f32<0>(base0 + offB[1]));
+                const float2 b01 = make_float2(lds_f32<4>(base0 + offB[0]), lds_f32<4>(base0 + offB[1]));
+                const float2 b10 = make_float2(lds_f32<0>(base1 + offB[0]), lds_f32<0>(base1 + offB[1]));
+                const float2 b11 = make_float2(lds_f32<4>(base1 + offB[0]), lds_f32<4>(base1 + offB[1]));
+                const float2 va = lerp2(wy2, lerp2(wx2, a00, a01), lerp2(wx2, a10, a11));
+                const float2 vb = lerp2(wy2, lerp2(wx2, b00, b01), lerp2(wx2, b10, b11));
+                const float2 r = lerp2(wz2, va, vb);
+                res[2 * j] = r.x;
+                res[2 * j + 1] = r.y;
+            }
+            bool bad = false;
+            if (CLEAN) {
+                float2 acc = make_float2(0.f, 0.f);   // stays 0 unless some result is non-finite
+#pragma unroll
+                for (int j = 0; j < NC2; ++j) acc = __ffma2_rn(make_float2(res[2 * j], res[2 * j + 1]), make_float2(0.f, 0.f), acc);
+                bad = !(acc.x == 0.f && acc.y == 0.f);
+            }
+            if (bad) {
+#pragma unroll
+                for (int c = 0; c < NC; ++c)
+                    if (nonfinite(res[c]))
+                        res[c] = tilt_exact_voxel(ring, &P, t0z + lz, t0y + warp + 8 * (c / IA), t0x + lane + 32 * (c % IA), oy0, ox0, 1);
+            }
+#pragma unroll
+            for (int rb = 0; rb < RB; ++rb) {
+                float *prow = pcol + (long long)(8 * rb) * P.ox;
+#pragma unroll
+                for (int ia = 0; ia < IA; ++ia) __stcs(prow + 32 * ia, res[rb * IA + ia]);
+            }
+        } else {
+            // mixed step: certainly outside -> cval, interior -> same arithmetic (scalar), rim -> exact voxel
+#pragma unroll
+            for (int c = 0; c < NC; ++c) {
+                const int zm = (int)(zf[c] >> 32), ym = (int)(yf[c] >> 32), xm = (int)(xf[c] >> 32);
+                float r = cval;
+                const bool outside = (unsigned)(zm + 2) > uz || (unsigned)(ym + 2) > uy || (unsigned)(xm + 2) > ux;
+                if (!outside && (live >> c & 1u)) {
+                    if ((unsigned)zm < hz && (unsigned)ym < hy && (unsigned)xm < hx) {
+                        const float wz = frac_weight((unsigned)zf[c]), wy = frac_weight((unsigned)yf[c]), wx = frac_weight((unsigned)xf[c]);
+                        const unsigned inpl = (unsigned)ym * pitch4 + ((unsigned)xm << 2);
+                        const unsigned offA = ((unsigned)zm & mask) * slot_bytes + inpl;
+                        const unsigned offB = ((unsigned)(zm + 1) & mask) * slot_bytes + inpl;
+                        const float a00 = lds_f32<0>(base0 + offA), a01 = lds_f32<4>(base0 + offA);
+                        const float a10 = lds_f32<0>(base1 + offA), a11 = lds_f32<4>(base1 + offA);
+                        const float b00 = lds_f32<0>(base0 + offB), b01 = lds_f32<4>(base0 + offB);
+                        const float b10 = lds_f32<0>(base1 + offB), b11 = lds_f32<4>(base1 + offB);
+                        const float xa0 = fmaf(wx, a01 - a00, a00), xa1 = fmaf(wx, a11 - a10, a10);
+                        const float xb0 = fmaf(wx, b01 - b00, b00), xb1 = fmaf(wx, b11 - b10, b10);
+                        const float va = fmaf(wy, xa1 - xa0, xa0), vb = fmaf(wy, xb1 - xb0, xb0);
+                        r = fmaf(wz, vb - va, va);
+                        if (CLEAN && nonfinite(r))
+                            r = tilt_exact_voxel(ring, &P, t0z + lz, t0y + warp + 8 * (c / IA), t0x + lane + 32 * (c % IA), oy0, ox0, 1);
+                    } else {
+                        r = tilt_exact_voxel(ring, &P, t0z + lz, t0y + warp + 8 * (c / IA), t0x + lane + 32 * (c % IA), oy0, ox0, CLEAN);
+                    }
+                }
+                if (live >> c & 1u) __stcs(pcol + (long long)(8 * (c / IA)) * P.ox + 32 * (c % IA), r);
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+            zf[c] += dzf;
+            yf[c] += dyf;
+            xf[c] += dxf;
+        }
+    }
+}
+
+template <int IA, int RB>
+static void (*pick_tilt(bool clean))(const CUtensorMap, const AffineParams, const TiltParams) {
+    return clean ? affine_tilt_kernel<IA, RB, true> : affine_tilt_kernel<IA, RB, false>;
+}
+
+// Host side: tile, ring depth and march length per launch; per-plane tensor map; one launch per z chunk.
+// Returns SHRIMPY_OK with *launched = false when the matrix/shape is not eligible (the caller falls back).
+int launch_affine_tilt(AffineParams P, int nan_to_zero, cudaStream_t s, bool *launched) {
+    *launched = false;
+    const double *M = P.M;
+    if ((reinterpret_cast<uintptr_t>(P.in) & 15u) != 0 || P.ix % 4 != 0 || (long long)P.oy * P.ox >= 2147483647LL ||
+        tensor_map_encoder() == nullptr)
+        return SHRIMPY_OK;
+    if (std::fabs(M[9]) > std::fabs(M[10])) return SHRIMPY_OK;   // lanes (o2) must walk input x
+    // 32.32 fixed point: |c| < 2^28 was checked by the caller; the per-step increments must fit too
+    for (int a = 0; a < 3; ++a)
+        if (!(std::fabs(M[4 * a]) < 1048576.0)) return SHRIMPY_OK;
+
+    static const int cand[][2] = {{2, 2}, {4, 1}, {2, 4}, {4, 2}, {2, 1}};
+    int forced[4] = {0, 0, 0, 0};   // IA, RB, ring, march length
+    if (const char *f = getenv("SHRIMPY_TILT_CFG")) sscanf(f, "%d,%d,%d,%d", &forced[0], &forced[1], &forced[2], &forced[3]);
+    double best = 1e300;
+    int bIA = 0, bRB = 0;
+    for (const auto &cd : cand) {
+        const int IA = cd[0], RB = cd[1];
+        if (forced[0] && (IA != forced[0] || RB != forced[1])) continue;
+        const int TY = 8 * RB, TX = 32 * IA;
+        const double zspread = std::fabs(M[1]) * (TY - 1) + std::fabs(M[2]) * (TX - 1);
+        const int window = (int)std::ceil(zspread) + 3;   // [floor(min) , floor(max) + 1] plus the 1e-6 margins
+        const int ctas = IA * RB <= 4 ? 3 : 2;
+        const long long budget = (ctas == 3 ? 72 : 108) * 1024;
+        for (int zc : {128, 64, 32, 16}) {
+            if (forced[3] && zc != forced[3]) continue;
+            const int ZC = std::min(zc, std::max(P.oz, 1));
+            const long long BY = (long long)std::ceil(std::fabs(M[4]) * (ZC - 1) + std::fabs(M[5]) * (TY - 1) + std::fabs(M[6]) * (TX - 1)) + 4;
+            long long BX = (long long)std::ceil(std::fabs(M[8]) * (ZC - 1) + std::fabs(M[9]) * (TY - 1) + std::fabs(M[10]) * (TX - 1)) + 4;
+            BX = (BX + 3 + 3) / 4 * 4;
+            if (BY > 256 || BX > 256) continue;
+            const long long PB = (BY * BX + 31) / 32 * 32;
+            for (int rl = 4; rl >= 2; --rl) {
+                if (forced[2] && (1 << rl) != forced[2]) continue;
+                if ((1 << rl) < window + 2) break;   // at least two planes of read-ahead
+                const long long bytes = (PB << rl) * 4 + 128;
+                if (bytes > budget) continue;
+                // cost: staged elements per output voxel (+ the window refill of every extra launch), shallow rings
+                // and short marches are penalised
+                const int nch = (P.oz + ZC - 1) / ZC;
+                double cost = (double)(BY * BX) / (TY * TX) * (1.0 + (double)window * (nch - 1) / std::max(P.oz, 1));
+                cost += ((1 << rl) < window + 4 ? 0.2 : 0.0) + 0.02 * nch + (IA * RB == 8 ? 0.1 : 0.0);
+                if (cost < best) {
+                    best = cost; bIA = IA; bRB = RB;
+                    P.ring_log2 = rl; P.ZC = ZC;
+                    P.BY = (int)BY; P.BX = (int)BX; P.pitch = (int)BX; P.PB = (int)PB; P.BZ = 1;
+                    P.TY = TY; P.TX = TX;
+                }
+                break;
+            }
+        }
+    }
+    if (best == 1e300) return SHRIMPY_OK;
+    const int nchunks = (P.oz + P.ZC - 1) / P.ZC;
+    P.ZC = (P.oz + nchunks - 1) / nchunks;   // even chunks
+    P.tiles_x = (P.ox + P.TX - 1) / P.TX;
+    P.tiles_y = (P.oy + P.TY - 1) / P.TY;
+    P.tiles_z = nchunks;
+    if (P.tiles_y > 65535) return SHRIMPY_OK;
+
+    CUtensorMap tmap{};
+    const cuuint64_t gdim[3] = {(cuuint64_t)P.ix, (cuuint64_t)P.iy, (cuuint64_t)P.iz};
+    const cuuint64_t gstride[2] = {(cuuint64_t)P.ix * 4, (cuuint64_t)P.ix * P.iy * 4};
+    const cuuint32_t bdim[3] = {(cuuint32_t)P.BX, (cuuint32_t)P.BY, 1u};
+    const cuuint32_t estr[3] = {1u, 1u, 1u};
+    P.tma_bytes = bdim[0] * bdim[1] * 4u;
+    const CUresult rc = tensor_map_encoder()(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(P.in), gdim,
+                                             gstride, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (rc != CUDA_SUCCESS) return fail(SHRIMPY_ECUDA, "affine tilt: cuTensorMapEncodeTiled failed (%d)", (int)rc);
+
+    void (*kern)(const CUtensorMap, const AffineParams, const TiltParams) = nullptr;
+    const bool cl = nan_to_zero != 0;
+    if (bIA == 2 && bRB == 2) kern = pick_tilt<2, 2>(cl);
+    else if (bIA == 4 && bRB == 1) kern = pick_tilt<4, 1>(cl);
+    else if (bIA == 2 && bRB == 4) kern = pick_tilt<2, 4>(cl);
+    else if (bIA == 4 && bRB == 2) kern = pick_tilt<4, 2>(cl);
+    else if (bIA == 2 && bRB == 1) kern = pick_tilt<2, 1>(cl);
+    else return SHRIMPY_OK;
+    const size_t smem = ((size_t)P.PB << P.ring_log2) * sizeof(float) + 128;
+    if (getenv("SHRIMPY_DEBUG"))
+        fprintf(stderr, "[shrimpy] affine tilt IA=%d RB=%d ring=%d box=(%d,%d) PB=%d ZC=%d smem=%zu grid=(%d,%d) x %d launches\n", bIA,
+                bRB, 1 << P.ring_log2, P.BY, P.BX, P.PB, P.ZC, smem, P.tiles_x, P.tiles_y, nchunks);
+    if (smem + 4096 > 48 * 1024)
+        SHRIMPY_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    TiltParams Q{};
+    for (int a = 0; a < 3; ++a) Q.step_fix[a] = std::llrint(M[4 * a] * 4294967296.0);
+    Q.dir = M[0] < 0.0 ? -1 : 1;
+    for (int ch = 0; ch < nchunks; ++ch) {
+        Q.t0z = ch * P.ZC;
+        Q.nsteps = std::min(P.ZC, P.oz - Q.t0z);
+        kern<<<dim3((unsigned)P.tiles_x, (unsigned)P.tiles_y), kTiltThreads, smem, s>>>(tmap, P, Q);
+        count_launch();
+    }
+    SHRIMPY_CUDA_TRY(cudaGetLastError());
+    *launched = true;
+    return SHRIMPY_OK;
+}
+
+}  // namespace shrimpy

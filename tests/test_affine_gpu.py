@@ -192,6 +192,58 @@ def test_planar_wide_tiles_identity_and_shift(env):
     assert np.array_equal(got, want)
 
 
+TILT_CASES = {
+    "small_rotations": ([[1.0284, -0.0508, 0.0192, 0.4], [0.0545, 0.968, -0.0384, -1.2], [-0.0161, 0.0347, 1.0992, 2.3]], (40, 96, 132), (44, 90, 150)),
+    "downwards": ([[-0.93, 0.03, -0.02, 37.6], [0.02, 1.04, 0.05, -2.0], [0.01, -0.04, 0.91, 6.0]], (40, 96, 132), (44, 100, 140)),
+    "z_stretch": ([[0.47, 0.011, 0.017, 3.2], [-0.03, 0.9, 0.02, 4.0], [0.02, 0.01, 1.2, -7.5]], (30, 80, 200), (70, 97, 170)),
+    "z_squeeze": ([[2.3, -0.02, 0.03, -4.0], [0.1, 1.0, 0.0, 1.0], [0.0, 0.1, 1.0, -3.0]], (90, 64, 96), (45, 70, 101)),
+    "steep_tilt": ([[1.0, 0.21, -0.13, 2.0], [-0.2, 0.98, 0.0, 9.0], [0.12, 0.0, 0.99, 1.0]], (48, 120, 136), (50, 110, 130)),
+    "two_launches": ([[0.25, 0.004, -0.006, 1.1], [0.003, 1.0, 0.02, 0.2], [-0.004, -0.02, 1.0, 2.6]], (40, 40, 64), (150, 44, 70)),
+    "no_z_motion": ([[0.0, 0.05, 0.03, 3.3], [0.3, 1.0, 0.0, 0.0], [0.0, 0.0, 1.0, 0.0]], (12, 64, 64), (20, 60, 66)),
+}
+
+
+@pytest.mark.parametrize("case", sorted(TILT_CASES))
+@pytest.mark.parametrize("cfg", ["", "2,2,0,0", "4,1,0,32", "2,4,0,0", "4,2,0,16", "2,1,0,64"])
+def test_tilt_kernel_general_matrices(env, case, cfg, monkeypatch):
+    """General 3-D matrices through the marching tilt kernel (forced: an ineligible case is an error, not a silent
+    fallback): planes visited up- and downwards, z stretch / squeeze, steep tilt, marches split over several launches,
+    every tile shape; geometry bit-exact, values within the float32 lerp tolerance of scipy."""
+    _, _, o, _ = env
+    rows, shape_in, shape_out = TILT_CASES[case]
+    M = np.array(rows + [[0, 0, 0, 1.0]], dtype=np.float64)
+    rng = np.random.default_rng(len(case))
+    vol = rng.standard_normal(shape_in).astype(np.float32)
+    want = o.apply_affine_transform(vol, M, shape_out, cval=-3.0)
+    monkeypatch.setenv("SHRIMPY_AFFINE_KERNEL", "m!")
+    if cfg:
+        monkeypatch.setenv("SHRIMPY_TILT_CFG", cfg)
+    try:
+        got = _run(env, vol, M, shape_out, cval=-3.0)
+    except Exception as exc:   # a forced tile shape may not fit this matrix; the automatic choice must
+        if cfg and "not eligible" in str(exc):
+            pytest.skip(f"tile {cfg} does not fit {case}")
+        raise
+    assert_close_range(got, want, AFFINE_TOL, f"tilt {case} {cfg}")
+    assert np.array_equal(got == -3.0, want == -3.0)
+
+
+def test_tilt_kernel_nan_to_num(env, monkeypatch):
+    torch, register, o, _ = env
+    rng = np.random.default_rng(17)
+    vol = rng.standard_normal((16, 48, 64)).astype(np.float32)
+    vol[5, 20, 30] = np.nan
+    vol[9, 11, 40] = -np.inf
+    M = np.array(TILT_CASES["small_rotations"][0] + [[0, 0, 0, 1.0]])
+    want = o.apply_affine_transform(vol, M, vol.shape)
+    monkeypatch.setenv("SHRIMPY_AFFINE_KERNEL", "m!")
+    got = _run(env, vol, M, vol.shape)
+    assert np.isfinite(got).all()
+    far = np.abs(want) < 1e30
+    assert np.max(np.abs(got[far] - want[far])) <= 1e-5
+    assert np.array_equal(got == 0.0, want == 0.0)
+
+
 def test_medium_volume_vs_c_oracle(env):
     _, _, _, c = env
     rng = np.random.default_rng(8)
