@@ -137,8 +137,7 @@ __global__ void __launch_bounds__(kStreamThreads, (IA * RB <= 4) ? 3 : 2)
             const uint32_t ring_s = smem_u32(ring);   // (the consumers keep their own copy)
             for (int seq = 0; seq < T.nseq; ++seq) {
                 const int slot = seq & mask, round = seq >> ring_log2;
-                if (round > 0)
-                    while (!mbar_try_wait_s(empty_s + 8u * slot, (round - 1) & 1)) __nanosleep(64);
+                if (round > 0) mbar_wait_suspend_s(empty_s + 8u * slot, (round - 1) & 1, 2000u);
                 mbar_arrive_expect_tx_s(full_s + 8u * slot, P.tma_bytes);
                 tma_load_3d_s(ring_s + slot * slot_bytes, &tmap, ox0, oy0, T.zfirst + seq * T.zdir, full_s + 8u * slot);
             }

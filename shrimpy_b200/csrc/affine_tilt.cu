@@ -5,16 +5,18 @@
 // producer warp streams input planes through a shared-memory ring with one 2-D TMA box per plane -- but here the
 // z coordinate of a voxel depends on (o1, o2) too, so
 //   * a step needs a WINDOW of planes [floor(min cz), floor(max cz) + 1] over the tile; the window slides
-//     monotonically with o0, plane z lives in slot (z - 1) & (R - 1), and the per-step wait / release counts
-//     are tabulated per CTA in shared memory (float64 corner arithmetic, margins of 1e-6);
+//     monotonically with o0 and plane z lives in slot z & (R - 1);
 //   * the (y, x) footprint of the tile drifts with o0; the staged box covers the whole march of the launch
 //     (the host bounds the march length so that it fits);
-//   * all three coordinates advance per step in 32.32 fixed point (two integer adds per axis: the floor is the
-//     high word for free, the lerp weight is the low word).  The start value of a column is scipy's exact
-//     float64 coordinate; after <= 128 steps the drift is < 2e-8 voxel, harmless for a voxel at least one
-//     input voxel away from the rim of the input (the interpolant is continuous).  Every other voxel (rim
-//     shell, non-finite result) is recomputed from the output index with scipy's exact arithmetic and edge
-//     rule (tilt_exact_voxel); voxels with floor <= -2 or >= dim on some axis are certainly outside.
+//   * every CTA tabulates, per step (one thread per step, float64 corner arithmetic): the planes that must have
+//     landed / may be handed back, the coordinate of the tile's first voxel relative to (ring origin, box origin)
+//     in 9.23 fixed point, and a CLASS: "fast" (every voxel of the tile strictly inside the input: no per-voxel
+//     test at all), "outside" (constant fill) or "mixed" (the tile straddles the rim: every voxel goes through
+//     tilt_exact_voxel, scipy's exact arithmetic and edge rule from the output index).
+// A voxel of a fast step is  base(step) + offset(column)  in 32-bit fixed point: one integer add per axis; floor,
+// ring slot, in-box offset and the 23-bit lerp weight are bit fields of the sum.  Nothing accumulates: the error
+// against scipy's float64 coordinate is < 2e-7 voxel (the weight itself has 23 bits), harmless strictly inside the
+// volume because the interpolant is continuous; the inside/outside decision never depends on it.
 // Interior arithmetic is issued as packed float32 pairs over two columns of a thread (FFMA2 / FADD2).
 #include "affine_common.cuh"
 
@@ -31,15 +33,10 @@ constexpr int kTiltMaxSteps = 128;
 constexpr int kTiltMaxRing = 16;
 
 struct TiltParams {
-    long long step_fix[3];   // per-o0 coordinate increments (z, y, x), 32.32 fixed point
     int t0z, nsteps;         // output steps [t0z, t0z + nsteps) of this launch
     int dir;                 // +1: planes are visited upwards, -1: downwards
     int pad;
 };
-
-__device__ __forceinline__ float frac_weight(unsigned lo) {   // low word of a 32.32 coordinate -> [0, 1), 23 bits
-    return __uint_as_float((lo >> 9) | 0x3f800000u) - 1.0f;
-}
 
 // Exact voxel: scipy's coordinate arithmetic from the output index, exact edge rule, clamped taps, nan_to_num.
 __device__ __noinline__ float tilt_exact_voxel(const float *ring, const AffineParams *Pp, int o0, int o1, int o2, int oy0,
@@ -60,7 +57,7 @@ __device__ __noinline__ float tilt_exact_voxel(const float *ring, const AffinePa
     if (!in) return P.cval;
     const int mask = (1 << P.ring_log2) - 1;
     const int z1 = min(z0 + 1, P.iz - 1);
-    const float *pa = ring + (size_t)((z0 - 1) & mask) * P.PB, *pb = ring + (size_t)((z1 - 1) & mask) * P.PB;
+    const float *pa = ring + (size_t)(z0 & mask) * P.PB, *pb = ring + (size_t)(z1 & mask) * P.PB;
     const int dy = (y0 + 1 < P.iy) ? P.pitch : 0;
     const int dx = (x0 + 1 < P.ix) ? 1 : 0;
     const int q = min(max(y0 - oy0, 0), P.BY - 2) * P.pitch + min(max(x0 - ox0, 0), P.BX - 2);
@@ -78,6 +75,13 @@ __device__ __noinline__ float tilt_exact_voxel(const float *ring, const AffinePa
     return fmaf(wz, b1 - b0, b0);
 }
 
+// Per-step record of a CTA (built in the prologue, one thread per step).
+struct StepInfo {
+    unsigned bz, by, bx;   // coordinate of the tile's first voxel relative to (ring origin, box origin), 9.23 fixed point
+    unsigned ctl;          // bits 0-11: planes [0, need) must have landed; 12-23: planes [0, rel) may be handed back; 24-25: class
+};
+enum { kStepMixed = 0, kStepFast = 1, kStepOutside = 2 };
+
 // IA = items along o2 per lane (tile extent 32*IA), RB = rows per warp (tile extent 8*RB along o1).
 template <int IA, int RB, bool CLEAN>
 __global__ void __launch_bounds__(kTiltThreads, (IA * RB <= 4) ? 3 : 2)
@@ -89,7 +93,7 @@ __global__ void __launch_bounds__(kTiltThreads, (IA * RB <= 4) ? 3 : 2)
 
     extern __shared__ __align__(128) float smem_raw[];
     __shared__ __align__(8) uint64_t full[kTiltMaxRing], empty[kTiltMaxRing];
-    __shared__ int2 win[kTiltMaxSteps];   // per step: planes [0, x) must have landed, planes [0, y) may be handed back
+    __shared__ __align__(16) StepInfo tab[kTiltMaxSteps];
     __shared__ int s_zmin, s_zmax;
     float *ring = smem_raw + (((128u - (smem_u32(smem_raw) & 127u)) & 127u) >> 2);
     const uint32_t full_s = smem_u32(full), empty_s = smem_u32(empty), ring_s = smem_u32(ring);
@@ -100,6 +104,7 @@ __global__ void __launch_bounds__(kTiltThreads, (IA * RB <= 4) ? 3 : 2)
     const int t0y = blockIdx.y * TY, t0x = blockIdx.x * TX, t0z = Q.t0z;
     const int nsteps = Q.nsteps, dir = Q.dir;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const bool tile_full = t0y + TY <= P.oy && t0x + TX <= P.ox;
 
     if (tid == 0) {
         s_zmin = 0x7fffffff;
@@ -127,20 +132,37 @@ __global__ void __launch_bounds__(kTiltThreads, (IA * RB <= 4) ? 3 : 2)
     const int oy0 = org[0], ox0 = org[1];
     __syncthreads();
 
-    // ---- per-step plane window of this tile -----------------------------------------------------------------------
-    int lo_k = 0, hi_k = 0, any = 0;
+    // ---- per-step record: plane window, class and start coordinate of this tile ----------------------------------------
+    int lo_k = 0, hi_k = 0, any = 0, cls = kStepMixed;
+    double c0[3] = {0.0, 0.0, 0.0};
     if (tid < nsteps) {
-        const double base = P.M[3] + (double)(t0z + tid) * P.M[0] + t0y * P.M[1] + t0x * P.M[2];
-        const double cmin = base + fmin(e1 * P.M[1], 0.0) + fmin(e2 * P.M[2], 0.0);
-        const double cmax = base + fmax(e1 * P.M[1], 0.0) + fmax(e2 * P.M[2], 0.0);
-        const int zlo = __double2int_rd(fmin(fmax(cmin - 1e-6, -1e9), 1e9));
-        const int zhi = __double2int_rd(fmin(fmax(cmax + 1e-6, -1e9), 1e9)) + 1;
-        any = zhi >= 0 && zlo <= P.iz - 1;
-        lo_k = min(max(zlo, 0), P.iz - 1);
-        hi_k = min(max(zhi, 0), P.iz - 1);
-        if (any) {
+        bool all_fast = true, some_out = false;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const double m1 = P.M[4 * a + 1], m2 = P.M[4 * a + 2];
+            // scipy's value at the tile's first voxel, and bounds over the tile
+            c0[a] = __dadd_rn(__dadd_rn(__dadd_rn(P.M[4 * a + 3], __dmul_rn((double)(t0z + tid), P.M[4 * a])),
+                                        __dmul_rn((double)t0y, m1)), __dmul_rn((double)t0x, m2));
+            const double cmin = c0[a] + fmin(e1 * m1, 0.0) + fmin(e2 * m2, 0.0);
+            const double cmax = c0[a] + fmax(e1 * m1, 0.0) + fmax(e2 * m2, 0.0);
+            const double dim = (double)(a == 0 ? P.iz : a == 1 ? P.iy : P.ix);
+            // corner arithmetic is good to ~1e-12 and the relative coordinates below to 2e-7: margins of 1e-5
+            all_fast = all_fast && cmin >= 1e-5 && cmax < dim - 1.0 - 1e-5;   // strictly inside, both taps exist, everywhere
+            some_out = some_out || cmax < -1e-5 || cmin > dim - 1.0 + 1e-5;   // c < 0 or c > dim - 1 everywhere
+            if (a == 0) {
+                const int zlo = __double2int_rd(fmin(fmax(cmin - 1e-6, -1e9), 1e9));
+                const int zhi = __double2int_rd(fmin(fmax(cmax + 1e-6, -1e9), 1e9)) + 1;
+                any = zhi >= 0 && zlo <= P.iz - 1;
+                lo_k = min(max(zlo, 0), P.iz - 1);
+                hi_k = min(max(zhi, 0), P.iz - 1);
+            }
+        }
+        cls = some_out ? kStepOutside : all_fast ? kStepFast : kStepMixed;
+        if (any && cls != kStepOutside) {
             atomicMin(&s_zmin, lo_k);
             atomicMax(&s_zmax, hi_k);
+        } else {
+            any = 0;
         }
     }
     __syncthreads();
@@ -148,9 +170,20 @@ __global__ void __launch_bounds__(kTiltThreads, (IA * RB <= 4) ? 3 : 2)
     const int nseq = zmax >= zmin ? zmax - zmin + 1 : 0;
     const int zstart = dir >= 0 ? zmin : zmax;   // plane of sequence number s is zstart + dir * s
     if (tid < nsteps) {
-        int2 w = make_int2(0, 0);
-        if (any) w = dir >= 0 ? make_int2(hi_k - zmin + 1, lo_k - zmin) : make_int2(zmax - lo_k + 1, zmax - hi_k);
-        win[tid] = w;
+        unsigned need = 0, rel = 0;
+        if (any) {
+            need = (unsigned)(dir >= 0 ? hi_k - zmin + 1 : zmax - lo_k + 1);
+            rel = (unsigned)(dir >= 0 ? lo_k - zmin : zmax - hi_k);
+        }
+        StepInfo e;
+        // relative 9.23 coordinates: z against a multiple of the ring size (only its low bits select the slot),
+        // (y, x) against the box origin; two's-complement wrap-around is harmless, interior voxels lie in [0, 512)
+        const double zorg = (double)((zmin == 0x7fffffff ? 0 : zmin) & ~mask);
+        e.bz = (unsigned)__double2ll_rd((c0[0] - zorg) * 8388608.0);
+        e.by = (unsigned)__double2ll_rd((c0[1] - (double)oy0) * 8388608.0);
+        e.bx = (unsigned)__double2ll_rd((c0[2] - (double)ox0) * 8388608.0);
+        e.ctl = need | (rel << 12) | ((unsigned)cls << 24);
+        tab[tid] = e;
     }
     __syncthreads();
 
@@ -159,10 +192,9 @@ __global__ void __launch_bounds__(kTiltThreads, (IA * RB <= 4) ? 3 : 2)
         if (lane == 0) {
             for (int seq = 0; seq < nseq; ++seq) {
                 const int z = zstart + dir * seq;
-                const unsigned slot = (unsigned)(z - 1) & mask;
+                const unsigned slot = (unsigned)z & mask;
                 const int round = seq >> ring_log2;
-                if (round > 0)
-                    while (!mbar_try_wait_s(empty_s + 8u * slot, (round - 1) & 1)) __nanosleep(64);
+                if (round > 0) mbar_wait_suspend_s(empty_s + 8u * slot, (round - 1) & 1, 2000u);
                 mbar_arrive_expect_tx_s(full_s + 8u * slot, P.tma_bytes);
                 tma_load_3d_s(ring_s + slot * slot_bytes, &tmap, ox0, oy0, z, full_s + 8u * slot);
             }
@@ -170,60 +202,47 @@ __global__ void __launch_bounds__(kTiltThreads, (IA * RB <= 4) ? 3 : 2)
         return;
     }
 
-    // ---- consumers: column start coordinates (scipy's exact float64 value at o0 = t0z, minus one, 32.32 fixed point) ----
-    long long zf[NC], yf[NC], xf[NC];
+    // ---- consumers: column offsets from the tile's first voxel, 9.23 fixed point (rounded once, never accumulated) ----
+    unsigned lz32[NC], ly32[NC], lx32[NC];
     unsigned live = 0;
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
-        const int o1 = t0y + warp + 8 * (c / IA), o2 = t0x + lane + 32 * (c % IA);
-        double cc[3];
-#pragma unroll
-        for (int a = 0; a < 3; ++a) {
-            double t = __dadd_rn(P.M[4 * a + 3], __dmul_rn((double)t0z, P.M[4 * a + 0]));
-            t = __dadd_rn(t, __dmul_rn((double)o1, P.M[4 * a + 1]));
-            cc[a] = __dadd_rn(t, __dmul_rn((double)o2, P.M[4 * a + 2]));
-        }
-        if (o1 < P.oy && o2 < P.ox) live |= 1u << c;
-        zf[c] = __double2ll_rd((cc[0] - 1.0) * 4294967296.0);
-        yf[c] = __double2ll_rd((cc[1] - 1.0) * 4294967296.0);
-        xf[c] = __double2ll_rd((cc[2] - 1.0) * 4294967296.0);
+        int l1 = warp + 8 * (c / IA), l2 = lane + 32 * (c % IA);
+        if (t0y + l1 < P.oy && t0x + l2 < P.ox) live |= 1u << c;
+        l1 = min(l1, (int)e1);   // columns beyond the output grid shadow the last live one (computed, never stored)
+        l2 = min(l2, (int)e2);
+        lz32[c] = (unsigned)__double2ll_rn(((double)l1 * P.M[1] + (double)l2 * P.M[2]) * 8388608.0);
+        ly32[c] = (unsigned)__double2ll_rn(((double)l1 * P.M[5] + (double)l2 * P.M[6]) * 8388608.0);
+        lx32[c] = (unsigned)__double2ll_rn(((double)l1 * P.M[9] + (double)l2 * P.M[10]) * 8388608.0);
     }
-    const long long dzf = Q.step_fix[0], dyf = Q.step_fix[1], dxf = Q.step_fix[2];
-    // high words hold floor(c) - 1: interior (both taps exist, nothing to clamp) <=> 0 <= floor - 1 <= dim - 4
-    const unsigned hz = (unsigned)max(P.iz - 3, 0), hy = (unsigned)max(P.iy - 3, 0), hx = (unsigned)max(P.ix - 3, 0);
-    const unsigned uz = (unsigned)P.iz, uy = (unsigned)P.iy, ux = (unsigned)P.ix;
-    // tap address = ring + slot * slot_bytes + ((y0 - oy0) * pitch + (x0 - ox0)) * 4, with y0 = ym + 1, x0 = xm + 1
-    const uint32_t base0 = ring_s + (unsigned)((1 - oy0) * pitch + (1 - ox0)) * 4u, base1 = base0 + pitch4;
+    const uint32_t base0 = ring_s, base1 = ring_s + pitch4;
 
     const long long plane = (long long)P.oy * P.ox;
     float *pcol = P.out + (long long)t0z * plane + (long long)(t0y + warp) * P.ox + t0x + lane;   // column c = 0
     const float cval = P.cval;
-    int ready = 0, released = 0;   // planes [0, ready) have landed; planes [0, released) were handed back
+    unsigned ready = 0, released = 0;             // planes [0, ready) have landed; planes [0, released) were handed back
+    unsigned rslot = (unsigned)zstart & mask;      // slot of plane `ready`
+    unsigned eslot = rslot;                        // slot of plane `released`
 
     for (int lz = 0; lz < nsteps; ++lz, pcol += plane) {
-        const int2 w = win[lz];
+        const StepInfo e = tab[lz];
+        const unsigned need = e.ctl & 0xfffu, rel = (e.ctl >> 12) & 0xfffu, cls = e.ctl >> 24;
 #pragma unroll 1
-        while (released < w.y) {
-            if (lane == 0) mbar_arrive_s(empty_s + 8u * ((unsigned)(zstart + dir * released - 1) & mask));
+        while (released < rel) {
+            if (lane == 0) mbar_arrive_s(empty_s + 8u * eslot);
+            eslot = (eslot + (unsigned)dir) & mask;
             ++released;
         }
 #pragma unroll 1
-        while (ready < w.x) {
-            mbar_wait_s(full_s + 8u * ((unsigned)(zstart + dir * ready - 1) & mask), (ready >> ring_log2) & 1);
+        while (ready < need) {
+            mbar_wait_s(full_s + 8u * rslot, (ready >> ring_log2) & 1u);
+            rslot = (rslot + (unsigned)dir) & mask;
             ++ready;
         }
 
-        // classification of this step's voxels
-        bool fast_all = true;
-#pragma unroll
-        for (int c = 0; c < NC; ++c) {
-            const unsigned zm = (unsigned)(zf[c] >> 32), ym = (unsigned)(yf[c] >> 32), xm = (unsigned)(xf[c] >> 32);
-            fast_all = fast_all && zm < hz && ym < hy && xm < hx;
-        }
-        fast_all = __all_sync(0xffffffffu, fast_all && live == (1u << NC) - 1u);
-
         float res[NC];
-        if (fast_all) {
+        if (cls == kStepFast) {
+            // every voxel of the tile is interior at this step: no tests, packed arithmetic
 #pragma unroll
             for (int j = 0; j < NC2; ++j) {
                 unsigned offA[2], offB[2];
@@ -231,13 +250,14 @@ __global__ void __launch_bounds__(kTiltThreads, (IA * RB <= 4) ? 3 : 2)
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     const int c = 2 * j + h;
-                    const int zm = (int)(zf[c] >> 32), ym = (int)(yf[c] >> 32), xm = (int)(xf[c] >> 32);
-                    wz[h] = frac_weight((unsigned)zf[c]);
-                    wy[h] = frac_weight((unsigned)yf[c]);
-                    wx[h] = frac_weight((unsigned)xf[c]);
-                    const unsigned inpl = (unsigned)ym * pitch4 + ((unsigned)xm << 2);
-                    offA[h] = ((unsigned)zm & mask) * slot_bytes + inpl;
-                    offB[h] = ((unsigned)(zm + 1) & mask) * slot_bytes + inpl;
+                    const unsigned cz = e.bz + lz32[c], cy = e.by + ly32[c], cx = e.bx + lx32[c];
+                    wz[h] = __uint_as_float((cz & 0x007fffffu) | 0x3f800000u) - 1.0f;
+                    wy[h] = __uint_as_float((cy & 0x007fffffu) | 0x3f800000u) - 1.0f;
+                    wx[h] = __uint_as_float((cx & 0x007fffffu) | 0x3f800000u) - 1.0f;
+                    const unsigned inpl = (cy >> 23) * pitch4 + ((cx >> 21) & ~3u);
+                    const unsigned sa = (cz >> 23) & mask, sb = (sa + 1u) & mask;
+                    offA[h] = sa * slot_bytes + inpl;
+                    offB[h] = sb * slot_bytes + inpl;
                 }
                 const float2 wx2 = make_float2(wx[0], wx[1]), wy2 = make_float2(wy[0], wy[1]), wz2 = make_float2(wz[0], wz[1]);
                 const float2 a00 = make_float2(lds_f32<0>(base0 + offA[0]), lds_f32<0>(base0 + offA[1]));
@@ -254,19 +274,30 @@ __global__ void __launch_bounds__(kTiltThreads, (IA * RB <= 4) ? 3 : 2)
                 res[2 * j] = r.x;
                 res[2 * j + 1] = r.y;
             }
-            bool bad = false;
             if (CLEAN) {
                 float2 acc = make_float2(0.f, 0.f);   // stays 0 unless some result is non-finite
 #pragma unroll
                 for (int j = 0; j < NC2; ++j) acc = __ffma2_rn(make_float2(res[2 * j], res[2 * j + 1]), make_float2(0.f, 0.f), acc);
-                bad = !(acc.x == 0.f && acc.y == 0.f);
-            }
-            if (bad) {
+                if (!(acc.x == 0.f && acc.y == 0.f)) {
 #pragma unroll
-                for (int c = 0; c < NC; ++c)
-                    if (nonfinite(res[c]))
-                        res[c] = tilt_exact_voxel(ring, &P, t0z + lz, t0y + warp + 8 * (c / IA), t0x + lane + 32 * (c % IA), oy0, ox0, 1);
+                    for (int c = 0; c < NC; ++c)
+                        if (nonfinite(res[c]))
+                            res[c] = tilt_exact_voxel(ring, &P, t0z + lz, t0y + warp + 8 * (c / IA), t0x + lane + 32 * (c % IA), oy0, ox0, 1);
+                }
             }
+        } else if (cls == kStepOutside) {
+#pragma unroll
+            for (int c = 0; c < NC; ++c) res[c] = cval;
+        } else {
+            // the tile straddles the rim of the input (or of the output grid) at this step: every voxel exactly
+#pragma unroll
+            for (int c = 0; c < NC; ++c) {
+                res[c] = cval;
+                if (live >> c & 1u)
+                    res[c] = tilt_exact_voxel(ring, &P, t0z + lz, t0y + warp + 8 * (c / IA), t0x + lane + 32 * (c % IA), oy0, ox0, CLEAN);
+            }
+        }
+        if (tile_full) {
 #pragma unroll
             for (int rb = 0; rb < RB; ++rb) {
                 float *prow = pcol + (long long)(8 * rb) * P.ox;
@@ -274,40 +305,9 @@ __global__ void __launch_bounds__(kTiltThreads, (IA * RB <= 4) ? 3 : 2)
                 for (int ia = 0; ia < IA; ++ia) __stcs(prow + 32 * ia, res[rb * IA + ia]);
             }
         } else {
-            // mixed step: certainly outside -> cval, interior -> same arithmetic (scalar), rim -> exact voxel
 #pragma unroll
-            for (int c = 0; c < NC; ++c) {
-                const int zm = (int)(zf[c] >> 32), ym = (int)(yf[c] >> 32), xm = (int)(xf[c] >> 32);
-                float r = cval;
-                const bool outside = (unsigned)(zm + 2) > uz || (unsigned)(ym + 2) > uy || (unsigned)(xm + 2) > ux;
-                if (!outside && (live >> c & 1u)) {
-                    if ((unsigned)zm < hz && (unsigned)ym < hy && (unsigned)xm < hx) {
-                        const float wz = frac_weight((unsigned)zf[c]), wy = frac_weight((unsigned)yf[c]), wx = frac_weight((unsigned)xf[c]);
-                        const unsigned inpl = (unsigned)ym * pitch4 + ((unsigned)xm << 2);
-                        const unsigned offA = ((unsigned)zm & mask) * slot_bytes + inpl;
-                        const unsigned offB = ((unsigned)(zm + 1) & mask) * slot_bytes + inpl;
-                        const float a00 = lds_f32<0>(base0 + offA), a01 = lds_f32<4>(base0 + offA);
-                        const float a10 = lds_f32<0>(base1 + offA), a11 = lds_f32<4>(base1 + offA);
-                        const float b00 = lds_f32<0>(base0 + offB), b01 = lds_f32<4>(base0 + offB);
-                        const float b10 = lds_f32<0>(base1 + offB), b11 = lds_f32<4>(base1 + offB);
-                        const float xa0 = fmaf(wx, a01 - a00, a00), xa1 = fmaf(wx, a11 - a10, a10);
-                        const float xb0 = fmaf(wx, b01 - b00, b00), xb1 = fmaf(wx, b11 - b10, b10);
-                        const float va = fmaf(wy, xa1 - xa0, xa0), vb = fmaf(wy, xb1 - xb0, xb0);
-                        r = fmaf(wz, vb - va, va);
-                        if (CLEAN && nonfinite(r))
-                            r = tilt_exact_voxel(ring, &P, t0z + lz, t0y + warp + 8 * (c / IA), t0x + lane + 32 * (c % IA), oy0, ox0, 1);
-                    } else {
-                        r = tilt_exact_voxel(ring, &P, t0z + lz, t0y + warp + 8 * (c / IA), t0x + lane + 32 * (c % IA), oy0, ox0, CLEAN);
-                    }
-                }
-                if (live >> c & 1u) __stcs(pcol + (long long)(8 * (c / IA)) * P.ox + 32 * (c % IA), r);
-            }
-        }
-#pragma unroll
-        for (int c = 0; c < NC; ++c) {
-            zf[c] += dzf;
-            yf[c] += dyf;
-            xf[c] += dxf;
+            for (int c = 0; c < NC; ++c)
+                if (live >> c & 1u) __stcs(pcol + (long long)(8 * (c / IA)) * P.ox + 32 * (c % IA), res[c]);
         }
     }
 }
@@ -326,9 +326,7 @@ int launch_affine_tilt(AffineParams P, int nan_to_zero, cudaStream_t s, bool *la
         tensor_map_encoder() == nullptr)
         return SHRIMPY_OK;
     if (std::fabs(M[9]) > std::fabs(M[10])) return SHRIMPY_OK;   // lanes (o2) must walk input x
-    // 32.32 fixed point: |c| < 2^28 was checked by the caller; the per-step increments must fit too
-    for (int a = 0; a < 3; ++a)
-        if (!(std::fabs(M[4 * a]) < 1048576.0)) return SHRIMPY_OK;
+    if (!(std::fabs(M[0]) <= 16.0)) return SHRIMPY_OK;   // plane counts of a march are kept in 12 bits
 
     static const int cand[][2] = {{2, 2}, {4, 1}, {2, 4}, {4, 2}, {2, 1}};
     int forced[4] = {0, 0, 0, 0};   // IA, RB, ring, march length
@@ -356,11 +354,12 @@ int launch_affine_tilt(AffineParams P, int nan_to_zero, cudaStream_t s, bool *la
                 if ((1 << rl) < window + 2) break;   // at least two planes of read-ahead
                 const long long bytes = (PB << rl) * 4 + 128;
                 if (bytes > budget) continue;
-                // cost: staged elements per output voxel (+ the window refill of every extra launch), shallow rings
-                // and short marches are penalised
+                // cost model (measured on config 3): the kernel is issue-bound, so the staged volume per output
+                // voxel matters little; every extra launch refills the plane window; 4 columns per thread
+                // (3 CTAs per SM) beat 8; a ring without slack stalls the producer
                 const int nch = (P.oz + ZC - 1) / ZC;
-                double cost = (double)(BY * BX) / (TY * TX) * (1.0 + (double)window * (nch - 1) / std::max(P.oz, 1));
-                cost += ((1 << rl) < window + 4 ? 0.2 : 0.0) + 0.02 * nch + (IA * RB == 8 ? 0.1 : 0.0);
+                double cost = 1.0 + 0.15 * (double)(BY * BX) / (TY * TX) + 0.1 * (nch - 1) * (1.0 + (double)window / ZC);
+                cost += ((1 << rl) < window + 4 ? 0.2 : 0.0) + (IA * RB == 8 ? 0.3 : 0.0) + (IA * RB == 2 ? 0.15 : 0.0);
                 if (cost < best) {
                     best = cost; bIA = IA; bRB = RB;
                     P.ring_log2 = rl; P.ZC = ZC;
@@ -405,7 +404,6 @@ int launch_affine_tilt(AffineParams P, int nan_to_zero, cudaStream_t s, bool *la
     if (smem + 4096 > 48 * 1024)
         SHRIMPY_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     TiltParams Q{};
-    for (int a = 0; a < 3; ++a) Q.step_fix[a] = std::llrint(M[4 * a] * 4294967296.0);
     Q.dir = M[0] < 0.0 ? -1 : 1;
     for (int ch = 0; ch < nchunks; ++ch) {
         Q.t0z = ch * P.ZC;

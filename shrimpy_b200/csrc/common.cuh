@@ -107,6 +107,23 @@ __device__ __forceinline__ bool mbar_try_wait_s(uint32_t bar, uint32_t parity) {
     return ok != 0;
 }
 
+// Producer-side wait: the thread is suspended by the hardware for up to `ns` per attempt instead of spinning
+// (a spinning producer lane was measured at 13 % of all issued instructions of the streaming kernels).
+__device__ __forceinline__ void mbar_wait_suspend_s(uint32_t bar, uint32_t parity, uint32_t ns) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity), "r"(ns)
+            : "memory");
+    } while (!ok);
+}
+
 __device__ __forceinline__ void mbar_wait_s(uint32_t bar, uint32_t parity) {
     while (!mbar_try_wait_s(bar, parity)) {
     }
