@@ -82,14 +82,29 @@ struct StepInfo {
 };
 enum { kStepMixed = 0, kStepFast = 1, kStepOutside = 2 };
 
-// IA = items along o2 per lane (tile extent 32*IA), RB = rows per warp (tile extent 8*RB along o1).
-template <int IA, int RB, bool CLEAN>
+__device__ __forceinline__ void tilt_consumer_sync() {
+    asm volatile("bar.sync 1, %0;" ::"n"(kTiltConsumers) : "memory");
+}
+
+// 23 fraction bits of a 9.23 coordinate -> lerp weight in [0, 1): (c & 0x7fffff) | 0x3f800000 as ONE LOP3 (the
+// constant 1.0f sits in a register), minus 1.
+__device__ __forceinline__ float frac23(unsigned c, unsigned one_bits) {
+    unsigned r;
+    asm("lop3.b32 %0, %1, 0x007fffff, %2, 0xEA;" : "=r"(r) : "r"(c), "r"(one_bits));
+    return __uint_as_float(r) - 1.0f;
+}
+
+// IA = items along the lane axis (tile extent 32*IA), RB = rows per warp (tile extent 8*RB along the other axis).
+// Lanes run along o2, or along o1 when input x follows o1 (SWAP: ~90 degree in-plane maps); then a step's results
+// are transposed through a double-buffered shared tile so that global stores stay coalesced along o2.
+template <int IA, int RB, bool SWAP, bool CLEAN>
 __global__ void __launch_bounds__(kTiltThreads, (IA * RB <= 4) ? 3 : 2)
     affine_tilt_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ AffineParams P,
                        const __grid_constant__ TiltParams Q) {
     constexpr int NC = IA * RB, NC2 = NC / 2;
     static_assert(NC % 2 == 0 && NC <= 8, "columns are processed in packed pairs");
-    constexpr int TY = 8 * RB, TX = 32 * IA;
+    constexpr int LA = 32 * IA, LB = 8 * RB;
+    constexpr int TY = SWAP ? LA : LB, TX = SWAP ? LB : LA;
 
     extern __shared__ __align__(128) float smem_raw[];
     __shared__ __align__(8) uint64_t full[kTiltMaxRing], empty[kTiltMaxRing];
@@ -194,7 +209,8 @@ __global__ void __launch_bounds__(kTiltThreads, (IA * RB <= 4) ? 3 : 2)
                 const int z = zstart + dir * seq;
                 const unsigned slot = (unsigned)z & mask;
                 const int round = seq >> ring_log2;
-                if (round > 0) mbar_wait_suspend_s(empty_s + 8u * slot, (round - 1) & 1, 2000u);
+                if (round > 0)
+                    while (!mbar_try_wait_s(empty_s + 8u * slot, (round - 1) & 1)) __nanosleep(300);
                 mbar_arrive_expect_tx_s(full_s + 8u * slot, P.tma_bytes);
                 tma_load_3d_s(ring_s + slot * slot_bytes, &tmap, ox0, oy0, z, full_s + 8u * slot);
             }
@@ -207,7 +223,8 @@ __global__ void __launch_bounds__(kTiltThreads, (IA * RB <= 4) ? 3 : 2)
     unsigned live = 0;
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
-        int l1 = warp + 8 * (c / IA), l2 = lane + 32 * (c % IA);
+        const int la = lane + 32 * (c % IA), lb = warp + 8 * (c / IA);
+        int l1 = SWAP ? la : lb, l2 = SWAP ? lb : la;
         if (t0y + l1 < P.oy && t0x + l2 < P.ox) live |= 1u << c;
         l1 = min(l1, (int)e1);   // columns beyond the output grid shadow the last live one (computed, never stored)
         l2 = min(l2, (int)e2);
@@ -215,16 +232,19 @@ __global__ void __launch_bounds__(kTiltThreads, (IA * RB <= 4) ? 3 : 2)
         ly32[c] = (unsigned)__double2ll_rn(((double)l1 * P.M[5] + (double)l2 * P.M[6]) * 8388608.0);
         lx32[c] = (unsigned)__double2ll_rn(((double)l1 * P.M[9] + (double)l2 * P.M[10]) * 8388608.0);
     }
-    const uint32_t base0 = ring_s, base1 = ring_s + pitch4;
+    unsigned one_bits = 0x3f800000u;
+    asm volatile("" : "+r"(one_bits));   // keep 1.0f in a register (see frac23)
+    float *otile = ring + ((size_t)P.PB << ring_log2);   // SWAP only: 2 x LA x (LB + 1)
 
     const long long plane = (long long)P.oy * P.ox;
-    float *pcol = P.out + (long long)t0z * plane + (long long)(t0y + warp) * P.ox + t0x + lane;   // column c = 0
+    float *pstep = P.out + (long long)t0z * plane;                         // output plane of the current step
+    float *pcol = pstep + (long long)(t0y + warp) * P.ox + t0x + lane;      // !SWAP: this thread's column c = 0
     const float cval = P.cval;
     unsigned ready = 0, released = 0;             // planes [0, ready) have landed; planes [0, released) were handed back
     unsigned rslot = (unsigned)zstart & mask;      // slot of plane `ready`
     unsigned eslot = rslot;                        // slot of plane `released`
 
-    for (int lz = 0; lz < nsteps; ++lz, pcol += plane) {
+    for (int lz = 0; lz < nsteps; ++lz, pcol += plane, pstep += plane) {
         const StepInfo e = tab[lz];
         const unsigned need = e.ctl & 0xfffu, rel = (e.ctl >> 12) & 0xfffu, cls = e.ctl >> 24;
 #pragma unroll 1
@@ -251,23 +271,23 @@ __global__ void __launch_bounds__(kTiltThreads, (IA * RB <= 4) ? 3 : 2)
                 for (int h = 0; h < 2; ++h) {
                     const int c = 2 * j + h;
                     const unsigned cz = e.bz + lz32[c], cy = e.by + ly32[c], cx = e.bx + lx32[c];
-                    wz[h] = __uint_as_float((cz & 0x007fffffu) | 0x3f800000u) - 1.0f;
-                    wy[h] = __uint_as_float((cy & 0x007fffffu) | 0x3f800000u) - 1.0f;
-                    wx[h] = __uint_as_float((cx & 0x007fffffu) | 0x3f800000u) - 1.0f;
-                    const unsigned inpl = (cy >> 23) * pitch4 + ((cx >> 21) & ~3u);
+                    wz[h] = frac23(cz, one_bits);
+                    wy[h] = frac23(cy, one_bits);
+                    wx[h] = frac23(cx, one_bits);
+                    const unsigned inpl = (cy >> 23) * pitch4 + (ring_s + ((cx >> 23) << 2));   // shared address of the first tap in slot 0
                     const unsigned sa = (cz >> 23) & mask, sb = (sa + 1u) & mask;
                     offA[h] = sa * slot_bytes + inpl;
                     offB[h] = sb * slot_bytes + inpl;
                 }
                 const float2 wx2 = make_float2(wx[0], wx[1]), wy2 = make_float2(wy[0], wy[1]), wz2 = make_float2(wz[0], wz[1]);
-                const float2 a00 = make_float2(lds_f32<0>(base0 + offA[0]), lds_f32<0>(base0 + offA[1]));
-                const float2 a01 = make_float2(lds_f32<4>(base0 + offA[0]), lds_f32<4>(base0 + offA[1]));
-                const float2 a10 = make_float2(lds_f32<0>(base1 + offA[0]), lds_f32<0>(base1 + offA[1]));
-                const float2 a11 = make_float2(lds_f32<4>(base1 + offA[0]), lds_f32<4>(base1 + offA[1]));
-                const float2 b00 = make_float2(lds_f32<0>(base0 + offB[0]), lds_f32<0>(base0 + offB[1]));
-                const float2 b01 = make_float2(lds_f32<4>(base0 + offB[0]), lds_f32<4>(base0 + offB[1]));
-                const float2 b10 = make_float2(lds_f32<0>(base1 + offB[0]), lds_f32<0>(base1 + offB[1]));
-                const float2 b11 = make_float2(lds_f32<4>(base1 + offB[0]), lds_f32<4>(base1 + offB[1]));
+                const float2 a00 = make_float2(lds_f32<0>(offA[0]), lds_f32<0>(offA[1]));
+                const float2 a01 = make_float2(lds_f32<4>(offA[0]), lds_f32<4>(offA[1]));
+                const float2 a10 = make_float2(lds_f32<0>(offA[0] + pitch4), lds_f32<0>(offA[1] + pitch4));
+                const float2 a11 = make_float2(lds_f32<4>(offA[0] + pitch4), lds_f32<4>(offA[1] + pitch4));
+                const float2 b00 = make_float2(lds_f32<0>(offB[0]), lds_f32<0>(offB[1]));
+                const float2 b01 = make_float2(lds_f32<4>(offB[0]), lds_f32<4>(offB[1]));
+                const float2 b10 = make_float2(lds_f32<0>(offB[0] + pitch4), lds_f32<0>(offB[1] + pitch4));
+                const float2 b11 = make_float2(lds_f32<4>(offB[0] + pitch4), lds_f32<4>(offB[1] + pitch4));
                 const float2 va = lerp2(wy2, lerp2(wx2, a00, a01), lerp2(wx2, a10, a11));
                 const float2 vb = lerp2(wy2, lerp2(wx2, b00, b01), lerp2(wx2, b10, b11));
                 const float2 r = lerp2(wz2, va, vb);
@@ -282,7 +302,8 @@ __global__ void __launch_bounds__(kTiltThreads, (IA * RB <= 4) ? 3 : 2)
 #pragma unroll
                     for (int c = 0; c < NC; ++c)
                         if (nonfinite(res[c]))
-                            res[c] = tilt_exact_voxel(ring, &P, t0z + lz, t0y + warp + 8 * (c / IA), t0x + lane + 32 * (c % IA), oy0, ox0, 1);
+                            res[c] = tilt_exact_voxel(ring, &P, t0z + lz, t0y + (SWAP ? lane + 32 * (c % IA) : warp + 8 * (c / IA)),
+                                                      t0x + (SWAP ? warp + 8 * (c / IA) : lane + 32 * (c % IA)), oy0, ox0, 1);
                 }
             }
         } else if (cls == kStepOutside) {
@@ -294,10 +315,22 @@ __global__ void __launch_bounds__(kTiltThreads, (IA * RB <= 4) ? 3 : 2)
             for (int c = 0; c < NC; ++c) {
                 res[c] = cval;
                 if (live >> c & 1u)
-                    res[c] = tilt_exact_voxel(ring, &P, t0z + lz, t0y + warp + 8 * (c / IA), t0x + lane + 32 * (c % IA), oy0, ox0, CLEAN);
+                    res[c] = tilt_exact_voxel(ring, &P, t0z + lz, t0y + (SWAP ? lane + 32 * (c % IA) : warp + 8 * (c / IA)),
+                                                      t0x + (SWAP ? warp + 8 * (c / IA) : lane + 32 * (c % IA)), oy0, ox0, CLEAN);
             }
         }
-        if (tile_full) {
+        if (SWAP) {
+            float *ot = otile + (lz & 1) * (LA * (LB + 1));
+#pragma unroll
+            for (int c = 0; c < NC; ++c) ot[(lane + 32 * (c % IA)) * (LB + 1) + warp + 8 * (c / IA)] = res[c];
+            tilt_consumer_sync();   // one barrier per step: the other buffer is written while this one drains
+#pragma unroll
+            for (int idx = tid; idx < LA * LB; idx += kTiltConsumers) {
+                const int a = idx / LB, b = idx % LB;
+                const int o1 = t0y + a, o2 = t0x + b;
+                if (o1 < P.oy && o2 < P.ox) __stcs(pstep + (long long)o1 * P.ox + o2, ot[a * (LB + 1) + b]);
+            }
+        } else if (tile_full) {
 #pragma unroll
             for (int rb = 0; rb < RB; ++rb) {
                 float *prow = pcol + (long long)(8 * rb) * P.ox;
@@ -313,8 +346,9 @@ __global__ void __launch_bounds__(kTiltThreads, (IA * RB <= 4) ? 3 : 2)
 }
 
 template <int IA, int RB>
-static void (*pick_tilt(bool clean))(const CUtensorMap, const AffineParams, const TiltParams) {
-    return clean ? affine_tilt_kernel<IA, RB, true> : affine_tilt_kernel<IA, RB, false>;
+static void (*pick_tilt(bool swap, bool clean))(const CUtensorMap, const AffineParams, const TiltParams) {
+    return swap ? (clean ? affine_tilt_kernel<IA, RB, true, true> : affine_tilt_kernel<IA, RB, true, false>)
+                : (clean ? affine_tilt_kernel<IA, RB, false, true> : affine_tilt_kernel<IA, RB, false, false>);
 }
 
 // Host side: tile, ring depth and march length per launch; per-plane tensor map; one launch per z chunk.
@@ -325,22 +359,24 @@ int launch_affine_tilt(AffineParams P, int nan_to_zero, cudaStream_t s, bool *la
     if ((reinterpret_cast<uintptr_t>(P.in) & 15u) != 0 || P.ix % 4 != 0 || (long long)P.oy * P.ox >= 2147483647LL ||
         tensor_map_encoder() == nullptr)
         return SHRIMPY_OK;
-    if (std::fabs(M[9]) > std::fabs(M[10])) return SHRIMPY_OK;   // lanes (o2) must walk input x
+    const bool swap = std::fabs(M[9]) > std::fabs(M[10]);   // input x follows o1 more than o2: lanes along o1
     if (!(std::fabs(M[0]) <= 16.0)) return SHRIMPY_OK;   // plane counts of a march are kept in 12 bits
 
-    static const int cand[][2] = {{2, 2}, {4, 1}, {2, 4}, {4, 2}, {2, 1}};
+    // (IA, RB): !swap: tile = (8 RB) x (32 IA) in (o1, o2); swap: (32 IA) x (8 RB), RB >= 4 so that drained rows are >= 128 bytes
+    static const int cand_plain[][2] = {{2, 2}, {4, 1}, {2, 4}, {4, 2}, {2, 1}};
+    static const int cand_swap[][2] = {{1, 4}, {1, 8}, {2, 4}, {0, 0}, {0, 0}};
     int forced[4] = {0, 0, 0, 0};   // IA, RB, ring, march length
     if (const char *f = getenv("SHRIMPY_TILT_CFG")) sscanf(f, "%d,%d,%d,%d", &forced[0], &forced[1], &forced[2], &forced[3]);
     double best = 1e300;
     int bIA = 0, bRB = 0;
-    for (const auto &cd : cand) {
-        const int IA = cd[0], RB = cd[1];
-        if (forced[0] && (IA != forced[0] || RB != forced[1])) continue;
-        const int TY = 8 * RB, TX = 32 * IA;
+    for (int k = 0; k < 5; ++k) {
+        const int IA = swap ? cand_swap[k][0] : cand_plain[k][0], RB = swap ? cand_swap[k][1] : cand_plain[k][1];
+        if (IA == 0 || (forced[0] && (IA != forced[0] || RB != forced[1]))) continue;
+        const int TY = swap ? 32 * IA : 8 * RB, TX = swap ? 8 * RB : 32 * IA;
+        const long long otile = swap ? 2LL * (32 * IA) * (8 * RB + 1) : 0;
         const double zspread = std::fabs(M[1]) * (TY - 1) + std::fabs(M[2]) * (TX - 1);
         const int window = (int)std::ceil(zspread) + 3;   // [floor(min) , floor(max) + 1] plus the 1e-6 margins
-        const int ctas = IA * RB <= 4 ? 3 : 2;
-        const long long budget = (ctas == 3 ? 72 : 108) * 1024;
+        const long long budget = 108 * 1024;   // two CTAs per SM at least; three when the ring is small enough
         for (int zc : {128, 64, 32, 16}) {
             if (forced[3] && zc != forced[3]) continue;
             const int ZC = std::min(zc, std::max(P.oz, 1));
@@ -352,7 +388,7 @@ int launch_affine_tilt(AffineParams P, int nan_to_zero, cudaStream_t s, bool *la
             for (int rl = 4; rl >= 2; --rl) {
                 if (forced[2] && (1 << rl) != forced[2]) continue;
                 if ((1 << rl) < window + 2) break;   // at least two planes of read-ahead
-                const long long bytes = (PB << rl) * 4 + 128;
+                const long long bytes = ((PB << rl) + otile) * 4 + 128;
                 if (bytes > budget) continue;
                 // cost model (measured on config 3): the kernel is issue-bound, so the staged volume per output
                 // voxel matters little; every extra launch refills the plane window; 4 columns per thread
@@ -360,11 +396,12 @@ int launch_affine_tilt(AffineParams P, int nan_to_zero, cudaStream_t s, bool *la
                 const int nch = (P.oz + ZC - 1) / ZC;
                 double cost = 1.0 + 0.15 * (double)(BY * BX) / (TY * TX) + 0.1 * (nch - 1) * (1.0 + (double)window / ZC);
                 cost += ((1 << rl) < window + 4 ? 0.2 : 0.0) + (IA * RB == 8 ? 0.3 : 0.0) + (IA * RB == 2 ? 0.15 : 0.0);
+                cost += (IA * RB <= 4 && bytes > 72 * 1024) ? 0.2 : 0.0;   // only two of the three possible CTAs fit
                 if (cost < best) {
                     best = cost; bIA = IA; bRB = RB;
                     P.ring_log2 = rl; P.ZC = ZC;
                     P.BY = (int)BY; P.BX = (int)BX; P.pitch = (int)BX; P.PB = (int)PB; P.BZ = 1;
-                    P.TY = TY; P.TX = TX;
+                    P.TY = TY; P.TX = TX; P.LA = 32 * IA; P.LB = 8 * RB;
                 }
                 break;
             }
@@ -391,16 +428,18 @@ int launch_affine_tilt(AffineParams P, int nan_to_zero, cudaStream_t s, bool *la
 
     void (*kern)(const CUtensorMap, const AffineParams, const TiltParams) = nullptr;
     const bool cl = nan_to_zero != 0;
-    if (bIA == 2 && bRB == 2) kern = pick_tilt<2, 2>(cl);
-    else if (bIA == 4 && bRB == 1) kern = pick_tilt<4, 1>(cl);
-    else if (bIA == 2 && bRB == 4) kern = pick_tilt<2, 4>(cl);
-    else if (bIA == 4 && bRB == 2) kern = pick_tilt<4, 2>(cl);
-    else if (bIA == 2 && bRB == 1) kern = pick_tilt<2, 1>(cl);
+    if (bIA == 2 && bRB == 2) kern = pick_tilt<2, 2>(swap, cl);
+    else if (bIA == 4 && bRB == 1) kern = pick_tilt<4, 1>(swap, cl);
+    else if (bIA == 2 && bRB == 4) kern = pick_tilt<2, 4>(swap, cl);
+    else if (bIA == 4 && bRB == 2) kern = pick_tilt<4, 2>(swap, cl);
+    else if (bIA == 2 && bRB == 1) kern = pick_tilt<2, 1>(swap, cl);
+    else if (bIA == 1 && bRB == 4) kern = pick_tilt<1, 4>(swap, cl);
+    else if (bIA == 1 && bRB == 8) kern = pick_tilt<1, 8>(swap, cl);
     else return SHRIMPY_OK;
-    const size_t smem = ((size_t)P.PB << P.ring_log2) * sizeof(float) + 128;
+    const size_t smem = (((size_t)P.PB << P.ring_log2) + (swap ? 2 * (size_t)P.LA * (P.LB + 1) : 0)) * sizeof(float) + 128;
     if (getenv("SHRIMPY_DEBUG"))
-        fprintf(stderr, "[shrimpy] affine tilt IA=%d RB=%d ring=%d box=(%d,%d) PB=%d ZC=%d smem=%zu grid=(%d,%d) x %d launches\n", bIA,
-                bRB, 1 << P.ring_log2, P.BY, P.BX, P.PB, P.ZC, smem, P.tiles_x, P.tiles_y, nchunks);
+        fprintf(stderr, "[shrimpy] affine tilt IA=%d RB=%d swap=%d ring=%d box=(%d,%d) PB=%d ZC=%d smem=%zu grid=(%d,%d) x %d launches\n", bIA,
+                bRB, (int)swap, 1 << P.ring_log2, P.BY, P.BX, P.PB, P.ZC, smem, P.tiles_x, P.tiles_y, nchunks);
     if (smem + 4096 > 48 * 1024)
         SHRIMPY_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     TiltParams Q{};

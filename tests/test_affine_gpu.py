@@ -199,12 +199,14 @@ TILT_CASES = {
     "z_squeeze": ([[2.3, -0.02, 0.03, -4.0], [0.1, 1.0, 0.0, 1.0], [0.0, 0.1, 1.0, -3.0]], (90, 64, 96), (45, 70, 101)),
     "steep_tilt": ([[1.0, 0.21, -0.13, 2.0], [-0.2, 0.98, 0.0, 9.0], [0.12, 0.0, 0.99, 1.0]], (48, 120, 136), (50, 110, 130)),
     "two_launches": ([[0.25, 0.004, -0.006, 1.1], [0.003, 1.0, 0.02, 0.2], [-0.004, -0.02, 1.0, 2.6]], (40, 40, 64), (150, 44, 70)),
+    "rot90_tilt": ([[1.0, 0.03, -0.02, 1.5], [0.02, 0.01, -1.288, 170.0], [-0.015, 1.288, 0.02, -3.0]], (30, 140, 136), (28, 100, 100)),
+    "rot270_tilt_down": ([[-0.8, -0.02, 0.04, 25.0], [0.03, -0.02, 0.9, 3.0], [0.01, -1.1, 0.03, 130.0]], (30, 120, 132), (33, 110, 125)),
     "no_z_motion": ([[0.0, 0.05, 0.03, 3.3], [0.3, 1.0, 0.0, 0.0], [0.0, 0.0, 1.0, 0.0]], (12, 64, 64), (20, 60, 66)),
 }
 
 
 @pytest.mark.parametrize("case", sorted(TILT_CASES))
-@pytest.mark.parametrize("cfg", ["", "2,2,0,0", "4,1,0,32", "2,4,0,0", "4,2,0,16", "2,1,0,64"])
+@pytest.mark.parametrize("cfg", ["", "2,2,0,0", "4,1,0,32", "2,4,0,0", "4,2,0,16", "2,1,0,64", "1,4,0,0", "1,8,0,32"])
 def test_tilt_kernel_general_matrices(env, case, cfg, monkeypatch):
     """General 3-D matrices through the marching tilt kernel (forced: an ineligible case is an error, not a silent
     fallback): planes visited up- and downwards, z stretch / squeeze, steep tilt, marches split over several launches,

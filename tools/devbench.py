@@ -95,7 +95,11 @@ if __name__ == "__main__":
         Mg[:3, 3] = [0.4, -1.2, 2.3]
         M90 = np.array([[1.0, 0, 0, 3.5], [0, 0, -1.288, 2040.0], [0, 1.288, 0, -20.0], [0, 0, 0, 1]])
         Mi = np.eye(4)
-        for name, M, oshape in (("identity", Mi, shape), ("general", Mg, shape), ("rot90", M90, (100, 2048, 1279))):
+        M90t = M90.copy()
+        M90t[0, 1:3] = [0.02, -0.015]
+        M90t[1, 0], M90t[2, 0] = 0.03, -0.02
+        for name, M, oshape in (("identity", Mi, shape), ("general", Mg, shape), ("rot90", M90, (100, 2048, 1279)),
+                                ("rot90tilt", M90t, (100, 2048, 1279))):
             out = torch.empty(oshape, device="cuda")
             if os.environ.get("DEVBENCH_ONCE"):
                 register.affine_transform_zyx(vol, M, oshape, out=out)
