@@ -306,10 +306,60 @@ def run_ours(args):
         "gpu_launches": int(launches),
         "clocks": clocks.summary(),
     }
+    if world == 1:
+        del raws, outs, h_raw, h_out
+        torch.cuda.empty_cache()
+        line["affine_registration"] = affine_block(peak)
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline_block()
     print(json.dumps(line), flush=True)
     return 0
+
+
+def affine_block(peak):
+    """BASELINE.json configs[2] beside the headline: float32 (107, 2048, 2048) resampled with a 4x4 matrix, device
+    resident, CUDA events, median of 8 launches after 3 warm-ups (inputs + outputs of 2.8-3.6 GB exceed the L2)."""
+    import torch
+
+    from shrimpy_b200 import register
+
+    shape = (107, 2048, 2048)
+    vol = torch.randn(shape, device="cuda")
+    a, b, c = np.deg2rad([2.0, 1.0, 3.0])
+    Rz = np.array([[1, 0, 0], [0, np.cos(a), -np.sin(a)], [0, np.sin(a), np.cos(a)]])
+    Ry = np.array([[np.cos(b), 0, np.sin(b)], [0, 1, 0], [-np.sin(b), 0, np.cos(b)]])
+    Rx = np.array([[np.cos(c), -np.sin(c), 0], [np.sin(c), np.cos(c), 0], [0, 0, 1]])
+    Mg = np.eye(4)
+    Mg[:3, :3] = Rz @ Ry @ Rx @ np.diag([1.03, 0.97, 1.1])
+    Mg[:3, 3] = [0.4, -1.2, 2.3]
+    M90 = np.array([[1.0, 0, 0, 3.5], [0, 0, -1.288, 2040.0], [0, 1.288, 0, -20.0], [0, 0, 0, 1]])
+    M90t = M90.copy()
+    M90t[0, 1:3] = [0.02, -0.015]
+    M90t[1, 0], M90t[2, 0] = 0.03, -0.02
+    cases = (("in_plane_identity_like", np.eye(4), shape, "affine_stream_kernel"),
+             ("in_plane_rot90_x1.288_onto_deskewed_grid", M90, (100, 2048, 1279), "affine_stream_kernel (lanes along o1)"),
+             ("general_rot_2_1_3_deg_aniso_scale", Mg, shape, "affine_tilt_kernel"),
+             ("rot90_x1.288_with_tilt_onto_deskewed_grid", M90t, (100, 2048, 1279), "affine_tilt_kernel (lanes along o1)"))
+    res = {}
+    for name, M, oshape, kern in cases:
+        out = torch.empty(oshape, device="cuda")
+        for _ in range(3):
+            register.affine_transform_zyx(vol, M, oshape, out=out)
+        torch.cuda.synchronize()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(8)]
+        for e0, e1 in ev:
+            e0.record()
+            register.affine_transform_zyx(vol, M, oshape, out=out)
+            e1.record()
+        torch.cuda.synchronize()
+        ms = float(np.median([e0.elapsed_time(e1) for e0, e1 in ev]))
+        nbytes = (vol.numel() + out.numel()) * 4
+        res[name] = {"kernel": kern, "out_shape": list(oshape), "ms": ms, "gvoxel_out_per_s": out.numel() / ms / 1e6,
+                     "algorithmic_gbs": nbytes / ms / 1e6, "frac_of_hbm_peak": nbytes / ms / 1e6 / peak,
+                     "inside_fraction": float((out != 0).float().mean())}
+        del out
+    return {"workload": "affine registration resample of a float32 label-free volume (107,2048,2048) with a 4x4 matrix "
+                        "(BASELINE.json configs[2]); algorithmic bytes = (input + output voxels) x 4", "cases": res}
 
 
 def main():

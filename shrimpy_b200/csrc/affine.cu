@@ -4,20 +4,18 @@
 // (float64, products and sums rounded separately: scipy.ndimage.affine_transform's order),
 // outside (any c_a < 0 or c_a > dim_a - 1, strict) -> cval; order=1, mode="constant".
 //
-// Two kernels:
-//   affine_gather_kernel  one thread per output voxel, taps through the read-only global path.
-//                         Any matrix; used when the staged footprint of a tile would not fit.
-//   affine_tile_kernel    one CTA per output tile (TZ,TY,TX).  The input bounding box of the tile
-//                         (an affine image of a box is bounded by its 8 corners) is staged in
-//                         shared memory asynchronously: by ONE 3-D TMA box load when a warp's 32
-//                         consecutive o2 stay within a few input rows (near-identity transforms),
-//                         or by cp.async row copies at an ODD row pitch when lanes walk input y or z
-//                         (e.g. the in-plane 90 degree label-free -> fluorescence registration), so
-//                         the tap reads are bank-conflict-free either way.  Lanes own consecutive
-//                         o2 (coalesced stores); the 8 taps per voxel come from shared memory.
-//                         nan_to_num is applied lazily: a non-finite result (which every non-finite
-//                         tap produces) is recomputed from cleaned taps.  The host picks the tile
-//                         shape per matrix.
+// Dispatch (shrimpy_affine_device, bottom of this file), fastest first:
+//   affine_stream_kernel  (affine_stream.cu) block-diagonal matrices: z-streaming march, plane values reused.
+//   affine_tilt_kernel    (affine_tilt.cu)   general matrices whose z spread over a tile is a few planes.
+//   affine_tile_kernel    (here) any matrix whose tile footprint fits shared memory: one CTA per output tile
+//                         (TZ,TY,TX); the input bounding box of the tile (an affine image of a box is bounded
+//                         by its 8 corners) is staged by ONE 3-D TMA box load when a warp's 32 consecutive o2
+//                         stay within a few input rows, or by cp.async row copies at an ODD row pitch when
+//                         lanes walk input y or z, so the tap reads are bank-conflict-free either way.
+//                         nan_to_num is applied lazily: a non-finite result (which every non-finite tap
+//                         produces) is recomputed from cleaned taps.  The host picks the tile shape.
+//   affine_gather_kernel  (here) one thread per output voxel, taps through the read-only global path: any
+//                         matrix, shape and alignment.
 #include "affine_common.cuh"
 
 #include <algorithm>
@@ -299,201 +297,6 @@ __global__ void __launch_bounds__(kTileThreads, 2)
     }
 }
 
-// ---- planar kernel: block-diagonal matrices (z <-> z, (y,x) <-> (y,x)) --------------------------------
-//
-// The label-free -> fluorescence registration of a mantis acquisition is an in-plane 2-D affine (rotation by
-// ~90 degrees, scale, shear, shift) plus a z shift/scale: M[0][1] = M[0][2] = M[1][0] = M[2][0] = 0.  Then
-//   * the z coordinate, its floor, weight and inside test depend on o0 only: warp 0 tabulates them per tile,
-//     exactly (scipy's arithmetic, exact edge rule), so there is no z rim and no per-voxel float64 work;
-//   * the (y, x) coordinate of a column (o1, o2) is computed ONCE, exactly, and its bilinear value in an input
-//     plane is reused by consecutive o0 (the planes of step k+1 are usually {z_b, z_b+1} of step k);
-//   * lanes run along the output axis that walks input x (o2, or o1 for ~90 degree maps: SWAP), so the box is
-//     always staged by ONE dense TMA load and tap reads are conflict-free; with SWAP the plane of results is
-//     transposed through a double-buffered shared tile so that global stores stay coalesced along o2.
-// All threads step through o0 together (z outermost); a thread keeps NC columns in registers.
-struct ZEntry {
-    int za, zb;   // float offsets of the two tap planes inside the box
-    float wz;
-    int inside;
-};
-
-template <int IA, int RB, bool SWAP, bool CLEAN>   // IA = LA / 32 items along the lane axis, RB = LB / 8 rows per warp
-__global__ void __launch_bounds__(kTileThreads, (IA * RB <= 4) ? 3 : 2)
-    affine_planar_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ AffineParams P) {
-    constexpr int kMaxTZ = 32;
-    extern __shared__ __align__(128) float smem_raw[];
-    __shared__ ZEntry ztab[kMaxTZ];
-    __shared__ int s_org[3];
-    __shared__ __align__(8) uint64_t bar;
-    float *box = smem_raw + (((128u - (smem_u32(smem_raw) & 127u)) & 127u) >> 2);
-    const int pitch = P.pitch, zs = P.BY * pitch;
-    float *otile = box + P.BZ * zs;   // SWAP only: 2 x LA x (LB + 1)
-
-    const int LA = P.LA, LB = P.LB;
-    const int TY = SWAP ? LA : LB, TX = SWAP ? LB : LA;
-    const int tz = blockIdx.x % P.tiles_z, tx = blockIdx.x / P.tiles_z, ty = blockIdx.y;
-    const int t0z = tz * P.TZ, t0y = ty * TY, t0x = tx * TX;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int nz = min(P.TZ, P.oz - t0z);
-
-    // --- per-tile set-up on warp 0: z table (lane = step), box origin, TMA -----------------------------------
-    if (warp == 0) {
-        double cz = 0.0;
-        int z0 = 0, inside = 0;
-        float wz = 0.f;
-        if (lane < nz) {
-            cz = __dadd_rn(P.M[3], __dmul_rn((double)(t0z + lane), P.M[0]));   // + o1*0 + o2*0: exact scipy value
-            inside = split_coord(cz, P.iz, z0, wz);
-        }
-        int zmin = inside ? z0 : 0x3fffffff;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) zmin = min(zmin, __shfl_xor_sync(0xffffffffu, zmin, o));
-        const int bz0 = (zmin == 0x3fffffff) ? 0 : zmin;
-        if (lane < nz) {
-            const int z1 = min(z0 + 1, P.iz - 1);
-            ZEntry e;
-            e.za = inside ? min(z0 - bz0, P.BZ - 1) * zs : 0;
-            e.zb = inside ? min(z1 - bz0, P.BZ - 1) * zs : 0;
-            e.wz = wz;
-            e.inside = inside;
-            ztab[lane] = e;
-        }
-        if (lane == 0) {
-            // (y, x) box origin: minimum corner of the tile under the in-plane affine
-            const double e1 = (double)(min(t0y + TY, P.oy) - 1 - t0y), e2 = (double)(min(t0x + TX, P.ox) - 1 - t0x);
-            int org[3] = {bz0, 0, 0};
-#pragma unroll
-            for (int a = 1; a < 3; ++a) {
-                const double m1 = P.M[4 * a + 1], m2 = P.M[4 * a + 2];
-                double lo = P.M[4 * a + 3] + t0y * m1 + t0x * m2 + fmin(e1 * m1, 0.0) + fmin(e2 * m2, 0.0);
-                const int dim = a == 1 ? P.iy : P.ix;
-                org[a] = __double2int_rd(fmin(fmax(lo - 1e-6, -4.0), (double)dim));
-            }
-            org[2] &= ~3;   // TMA: 16-byte aligned start along x
-            s_org[0] = org[0]; s_org[1] = org[1]; s_org[2] = org[2];
-            mbar_init(&bar, 1);
-            fence_mbar_init();
-            mbar_arrive_expect_tx(&bar, P.tma_bytes);
-            tma_load_3d(smem_u32(box), &tmap, org[2], org[1], org[0], &bar);
-        }
-    }
-    __syncthreads();
-    const int oz0 = s_org[0], oy0 = s_org[1], ox0 = s_org[2];
-
-    // --- per-column set-up: exact (y, x) coordinate, floor, weights, classification -----------------------------
-    constexpr int NC = IA * RB;               // columns a thread keeps in registers
-    int qoff[NC];
-    float wy[NC], wx[NC];
-    unsigned fast_mask = 0, out_mask = 0, live_mask = 0;   // bit c: interior column / certainly outside / exists
-    const unsigned hy = (unsigned)max(P.iy - 3, 0), hx = (unsigned)max(P.ix - 3, 0);
-#pragma unroll
-    for (int c = 0; c < NC; ++c) {
-        const int a = lane + 32 * (c % IA), b = warp + 8 * (c / IA);
-        const int o1 = t0y + (SWAP ? a : b), o2 = t0x + (SWAP ? b : a);
-        qoff[c] = 0; wy[c] = 0.f; wx[c] = 0.f;
-        if (a < LA && b < LB && o1 < P.oy && o2 < P.ox) {
-            live_mask |= 1u << c;
-            // o0 * 0 contributes exactly +-0, so this is scipy's value for every o0
-            const double cy = __dadd_rn(__dadd_rn(P.M[7], __dmul_rn((double)o1, P.M[5])), __dmul_rn((double)o2, P.M[6]));
-            const double cx = __dadd_rn(__dadd_rn(P.M[11], __dmul_rn((double)o1, P.M[9])), __dmul_rn((double)o2, P.M[10]));
-            const int y0 = split_fast(cy, wy[c]), x0 = split_fast(cx, wx[c]);
-            if ((unsigned)(y0 - 1) < hy && (unsigned)(x0 - 1) < hx) {
-                fast_mask |= 1u << c;
-                qoff[c] = (y0 - oy0) * pitch + (x0 - ox0);
-            } else if ((unsigned)(y0 + 1) > (unsigned)P.iy || (unsigned)(x0 + 1) > (unsigned)P.ix) {
-                out_mask |= 1u << c;
-            }
-        }
-    }
-    const unsigned rim_mask = live_mask & ~fast_mask & ~out_mask;   // exact slow path whenever z is inside
-
-    mbar_wait(&bar, 0);
-
-    // --- march through o0 ------------------------------------------------------------------------------------------
-    float bA[NC], bB[NC];
-#pragma unroll
-    for (int c = 0; c < NC; ++c) bA[c] = bB[c] = 0.f;
-    int prev_a = -1, prev_b = -1;
-    const long long plane = (long long)P.oy * P.ox;
-    float *pbase = P.out + (long long)t0z * plane;   // start of output plane t0z (advanced per step)
-
-    auto plane_value = [&](int zoff, int c) -> float {
-        const float *q = box + zoff + qoff[c];
-        const float a0 = fmaf(wx[c], q[1] - q[0], q[0]);
-        const float a1 = fmaf(wx[c], q[pitch + 1] - q[pitch], q[pitch]);
-        return fmaf(wy[c], a1 - a0, a0);
-    };
-
-    for (int lz = 0; lz < nz; ++lz, pbase += plane) {
-        const ZEntry e = ztab[lz];
-        float res[NC];
-        unsigned rare = 0;
-        if (e.inside) {
-            // reuse the bilinear plane values of the previous step where the planes coincide (uniform branches)
-            if (e.za == prev_b && e.za != prev_a) {
-#pragma unroll
-                for (int c = 0; c < NC; ++c) bA[c] = bB[c];
-            } else if (e.za != prev_a) {
-#pragma unroll
-                for (int c = 0; c < NC; ++c) bA[c] = plane_value(e.za, c);
-            }
-            if (e.zb == e.za) {
-#pragma unroll
-                for (int c = 0; c < NC; ++c) bB[c] = bA[c];
-            } else if (!(e.zb == prev_b && e.za == prev_a)) {
-#pragma unroll
-                for (int c = 0; c < NC; ++c) bB[c] = plane_value(e.zb, c);
-            }
-            prev_a = e.za;
-            prev_b = e.zb;
-#pragma unroll
-            for (int c = 0; c < NC; ++c) {
-                const float v = fmaf(e.wz, bB[c] - bA[c], bA[c]);
-                res[c] = (fast_mask >> c & 1u) ? v : P.cval;
-                if (CLEAN && (fast_mask >> c & 1u) && (__float_as_uint(v) & 0x7f800000u) == 0x7f800000u) rare |= 1u << c;
-            }
-            rare |= rim_mask;
-        } else {
-#pragma unroll
-            for (int c = 0; c < NC; ++c) res[c] = P.cval;
-        }
-        if (!SWAP) {
-#pragma unroll
-            for (int c = 0; c < NC; ++c) {
-                const int a = lane + 32 * (c % IA), b = warp + 8 * (c / IA);
-                if (live_mask >> c & 1u) __stcs(pbase + (long long)(t0y + b) * P.ox + (t0x + a), res[c]);
-            }
-            while (rare) {   // exact patch of rim columns / non-finite taps (rare)
-                const int c = __ffs(rare) - 1;
-                rare &= rare - 1;
-                const int a = lane + 32 * (c % IA), b = warp + 8 * (c / IA);
-                __stcs(pbase + (long long)(t0y + b) * P.ox + (t0x + a),
-                       affine_edge_voxel(box, &P, t0z + lz, t0y + b, t0x + a, oz0, oy0, ox0, CLEAN));
-            }
-        } else {
-            float *ot = otile + (lz & 1) * (LA * (LB + 1));
-#pragma unroll
-            for (int c = 0; c < NC; ++c) {
-                const int a = lane + 32 * (c % IA), b = warp + 8 * (c / IA);
-                if (a < LA && b < LB) ot[a * (LB + 1) + b] = res[c];
-            }
-            while (rare) {
-                const int c = __ffs(rare) - 1;
-                rare &= rare - 1;
-                const int a = lane + 32 * (c % IA), b = warp + 8 * (c / IA);
-                ot[a * (LB + 1) + b] = affine_edge_voxel(box, &P, t0z + lz, t0y + a, t0x + b, oz0, oy0, ox0, CLEAN);
-            }
-            __syncthreads();   // one barrier per step: the other buffer is written while this one drains
-            // coalesced drain: rows = o1 (a), lanes along o2 (b)
-            for (int idx = threadIdx.x; idx < LA * LB; idx += kTileThreads) {
-                const int a = idx / LB, b = idx - a * LB;
-                const int o1 = t0y + a, o2 = t0x + b;
-                if (o1 < P.oy && o2 < P.ox) __stcs(pbase + (long long)o1 * P.ox + o2, ot[a * (LB + 1) + b]);
-            }
-        }
-    }
-}
-
 // Host: pick the output tile whose staged input box is smallest per output voxel.
 static bool choose_tile(AffineParams &P, int smem_limit, bool tma) {
     static const int cand[][3] = {{8, 16, 64}, {4, 16, 64}, {4, 8, 64},  {2, 16, 64},  {8, 8, 64},   {4, 32, 64},
@@ -568,7 +371,7 @@ extern "C" int shrimpy_affine_device(const float *d_in, float *d_out, int iz, in
                              std::fabs(M[4 * a + 2]) * ox;
         if (!(reach < 134217728.0)) want_gather = true;
     }
-    // Block-diagonal matrix (z <-> z, (y,x) <-> (y,x)): the z-streaming kernel, else the planar tile kernel.
+    // Block-diagonal matrix (z <-> z, (y,x) <-> (y,x)): the z-streaming planar kernel (affine_stream.cu).
     if (!want_gather && (!force || force[0] == 's')) {
         bool launched = false;
         const int rc = launch_affine_stream(P, nan_to_zero, s, &launched);
@@ -582,80 +385,6 @@ extern "C" int shrimpy_affine_device(const float *d_in, float *d_out, int iz, in
         if (rc != SHRIMPY_OK || launched) return rc;
         if (force && force[1] == '!') return fail(SHRIMPY_EINVAL, "affine: the tilt kernel was forced but is not eligible");
     }
-    const bool planar_ok = !want_gather && !(force && force[0] != 'p') && M[1] == 0.0 && M[2] == 0.0 && M[4] == 0.0 &&
-                           M[8] == 0.0 && (reinterpret_cast<uintptr_t>(d_in) & 15u) == 0 && ix % 4 == 0 &&
-                           (long long)oy * ox < 2147483647LL && tensor_map_encoder() != nullptr;
-    if (planar_ok) {
-        const bool swap = std::fabs(M[9]) > std::fabs(M[10]);   // input x follows o1 more than o2: lanes along o1
-        // (TZ, LA, LB) with (LA/32, LB/8) in {(2,2), (1,4), (2,4), (1,8), (1,2)} -- the instantiated shapes
-        static const int cand[][3] = {{16, 64, 16}, {16, 32, 32}, {8, 64, 16}, {8, 32, 32}, {16, 64, 32}, {8, 64, 32},
-                                      {16, 32, 64}, {8, 32, 64}, {16, 32, 16}, {8, 32, 16}, {4, 32, 32}, {4, 64, 16},
-                                      {32, 32, 32}, {32, 64, 16}};
-        double best = 1e300;
-        int forced[3] = {0, 0, 0};
-        if (const char *f = getenv("SHRIMPY_PLANAR_TILE")) sscanf(f, "%d,%d,%d", &forced[0], &forced[1], &forced[2]);
-        for (const auto &c : cand) {
-            if (forced[0] && (c[0] != forced[0] || c[1] != forced[1] || c[2] != forced[2])) continue;
-            const int TZ = c[0], LA = c[1], LB = c[2];
-            if (swap && LB < 32) continue;                       // drained rows must be >= 128 bytes
-            const int TY = swap ? LA : LB, TX = swap ? LB : LA;
-            const long long BZ = (long long)std::ceil(std::fabs(M[0]) * (TZ - 1)) + 3;
-            const long long BY = (long long)std::ceil(std::fabs(M[5]) * (TY - 1) + std::fabs(M[6]) * (TX - 1)) + 3;
-            long long BX = (long long)std::ceil(std::fabs(M[9]) * (TY - 1) + std::fabs(M[10]) * (TX - 1)) + 3;
-            BX = (BX + 3 + 3) / 4 * 4;
-            if (BZ > 256 || BY > 256 || BX > 256) continue;
-            const long long otile = swap ? 2LL * LA * (LB + 1) : 0;
-            const long long bytes = (BZ * BY * BX + otile) * 4 + 128;
-            if (bytes > 100 * 1024) continue;   // at least 2 CTAs per SM
-            const double outputs = (double)TZ * TY * TX;
-            const double cost = (double)(BZ * BY * BX) / outputs + 512.0 / outputs + (bytes > 72 * 1024 ? 1.0 : 0.0);
-            if (cost < best) {
-                best = cost;
-                P.TZ = TZ; P.LA = LA; P.LB = LB; P.TY = TY; P.TX = TX;
-                P.BZ = (int)BZ; P.BY = (int)BY; P.BX = (int)BX; P.pitch = (int)BX;
-            }
-        }
-        if (best < 1e300) {
-            P.tiles_x = (ox + P.TX - 1) / P.TX;
-            P.tiles_y = (oy + P.TY - 1) / P.TY;
-            P.tiles_z = (oz + P.TZ - 1) / P.TZ;
-            if (P.tiles_y <= 65535 && (long long)P.tiles_x * P.tiles_z <= 2147483647LL) {
-                CUtensorMap tmap{};
-                const cuuint64_t gdim[3] = {(cuuint64_t)ix, (cuuint64_t)iy, (cuuint64_t)iz};
-                const cuuint64_t gstride[2] = {(cuuint64_t)ix * 4, (cuuint64_t)ix * iy * 4};
-                const cuuint32_t bdim[3] = {(cuuint32_t)P.BX, (cuuint32_t)P.BY, (cuuint32_t)P.BZ};
-                const cuuint32_t estr[3] = {1u, 1u, 1u};
-                P.tma_bytes = bdim[0] * bdim[1] * bdim[2] * 4u;
-                const CUresult rc = tensor_map_encoder()(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(d_in),
-                                                         gdim, gstride, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                                                         CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                                                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-                if (rc != CUDA_SUCCESS) return fail(SHRIMPY_ECUDA, "affine: cuTensorMapEncodeTiled failed (%d)", (int)rc);
-                const int ia = P.LA / 32, rb = P.LB / 8, nc = ia * rb;
-                const size_t smem = ((size_t)P.BZ * P.BY * P.BX + (swap ? 2 * (size_t)P.LA * (P.LB + 1) : 0)) * sizeof(float) + 128;
-                void (*kern)(const CUtensorMap, const AffineParams) = nullptr;
-#define SHRIMPY_PLANAR(I, R)                                                                                             \
-    (swap ? (nan_to_zero ? affine_planar_kernel<I, R, true, true> : affine_planar_kernel<I, R, true, false>)             \
-          : (nan_to_zero ? affine_planar_kernel<I, R, false, true> : affine_planar_kernel<I, R, false, false>))
-                kern = (ia == 2 && rb == 2)   ? SHRIMPY_PLANAR(2, 2)
-                       : (ia == 1 && rb == 4) ? SHRIMPY_PLANAR(1, 4)
-                       : (ia == 2 && rb == 4) ? SHRIMPY_PLANAR(2, 4)
-                       : (ia == 1 && rb == 8) ? SHRIMPY_PLANAR(1, 8)
-                                              : SHRIMPY_PLANAR(1, 2);
-#undef SHRIMPY_PLANAR
-                if (getenv("SHRIMPY_DEBUG"))
-                    fprintf(stderr, "[shrimpy] affine planar TZ=%d LA=%d LB=%d swap=%d B=(%d,%d,%d) nc=%d smem=%zu grid=(%d,%d)\n",
-                            P.TZ, P.LA, P.LB, (int)swap, P.BZ, P.BY, P.BX, nc, smem, P.tiles_x * P.tiles_z, P.tiles_y);
-                if (smem + 2048 > 48 * 1024)
-                    SHRIMPY_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                kern<<<dim3((unsigned)(P.tiles_x * P.tiles_z), (unsigned)P.tiles_y), kTileThreads, smem, s>>>(tmap, P);
-                count_launch();
-                SHRIMPY_CUDA_TRY(cudaGetLastError());
-                return SHRIMPY_OK;
-            }
-        }
-    }
-
     const int smem_limit = 56 * 1024;  // 4 CTAs per SM: staging of one tile overlaps the maths of others
     // TMA staging (dense pitch) when a warp's 32 consecutive o2 touch only a few input rows and the
     // tensor map constraints hold; otherwise cp.async rows at an odd pitch.
