@@ -192,6 +192,45 @@ def test_planar_wide_tiles_identity_and_shift(env):
     assert np.array_equal(got, want)
 
 
+STREAM_CASES = {
+    # name: (z row (scale, shift), in-plane angle, in-plane scale, input shape, output shape)
+    "long_march_up": ((0.13, 0.4), 7.0, 1.05, (40, 72, 96), (300, 70, 100)),
+    "long_march_down": ((-0.21, 38.7), 7.0, 0.95, (40, 72, 96), (200, 64, 90)),
+    "rot90_long": ((0.3, 0.2), 90.0, 1.288, (50, 96, 128), (170, 90, 70)),
+    "rot270_skip_planes": ((2.6, -1.0), 270.0, 0.8, (60, 96, 128), (30, 100, 110)),
+    "z_constant": ((0.0, 3.25), 3.0, 1.0, (8, 64, 64), (5, 64, 64)),
+}
+
+
+@pytest.mark.parametrize("case", sorted(STREAM_CASES))
+@pytest.mark.parametrize("cfg", ["", "4,2,8", "2,4,4", "2,2,8", "4,1,4", "2,1,8", "1,8,4", "1,4,8"])
+def test_stream_kernel_marches(env, case, cfg, monkeypatch):
+    """Block-diagonal matrices through the z-streaming kernel (forced): marches longer than one launch (> 128 output
+    planes), planes visited downwards, skipped planes (|z scale| > 2), a constant z, every tile shape and ring depth."""
+    _, _, o, _ = env
+    (zs, zt), angle, scale, shape_in, shape_out = STREAM_CASES[case]
+    th = np.deg2rad(angle)
+    R = scale * np.array([[np.cos(th), -np.sin(th)], [np.sin(th), np.cos(th)]])
+    M = np.eye(4)
+    M[0, 0], M[0, 3] = zs, zt
+    M[1:3, 1:3] = R
+    M[1:3, 3] = np.array([shape_in[1] / 2, shape_in[2] / 2]) - R @ np.array([shape_out[1] / 2, shape_out[2] / 2])
+    rng = np.random.default_rng(len(case) + 3)
+    vol = rng.standard_normal(shape_in).astype(np.float32)
+    want = o.apply_affine_transform(vol, M, shape_out, cval=2.5)
+    monkeypatch.setenv("SHRIMPY_AFFINE_KERNEL", "s!")
+    if cfg:
+        monkeypatch.setenv("SHRIMPY_STREAM_CFG", cfg)
+    try:
+        got = _run(env, vol, M, shape_out, cval=2.5)
+    except Exception as exc:   # a forced tile shape exists for one lane orientation only
+        if cfg and "not eligible" in str(exc):
+            pytest.skip(f"tile {cfg} does not apply to {case}")
+        raise
+    assert_close_range(got, want, AFFINE_TOL, f"stream {case} {cfg}")
+    assert np.array_equal(got == 2.5, want == 2.5)
+
+
 TILT_CASES = {
     "small_rotations": ([[1.0284, -0.0508, 0.0192, 0.4], [0.0545, 0.968, -0.0384, -1.2], [-0.0161, 0.0347, 1.0992, 2.3]], (40, 96, 132), (44, 90, 150)),
     "downwards": ([[-0.93, 0.03, -0.02, 37.6], [0.02, 1.04, 0.05, -2.0], [0.01, -0.04, 0.91, 6.0]], (40, 96, 132), (44, 100, 140)),
