@@ -7,10 +7,15 @@
 // Here the correction is expressed as a per-pixel scale  s[y,x] = mean(pattern) / pattern[y,x]  so that it
 // can be fused into the deskew kernel (the deskew interpolates along z only, so scaling commutes with it).
 //
-// median_z_kernel: a CTA stages a [Z][64 x] tile (row pitch padded by one bank), then each warp runs an
-// exact radix select per pixel column: every lane keeps ceil(Z/32) values in registers and the warp
-// narrows the answer one bit per step with a ballot-free count (popc of per-lane compares + warp add).
-// For even Z both middle order statistics are found and averaged (numpy.median / quantile(0.5) linear).
+// median_z_kernel: exact per-pixel median by byte-wise radix selection with shared-memory histograms.  A CTA owns
+// 64 consecutive pixels of one image row; per pass every thread walks its quarter of the scan axis (loads are
+// coalesced along x: the 64 pixels of a slice are 128 / 256 contiguous bytes) and counts one key byte of the keys
+// that still match the decided prefix into hist[byte][pixel] (the 32 lanes of a warp hit 32 different banks, so
+// the shared atomics never conflict).  Four threads per pixel then locate the bin holding the wanted rank.
+// uint16 needs 2 passes, float32 4; the slab of a CTA (Z x 64 pixels) is re-read from L1/L2, DRAM sees it once.
+// For even Z the upper middle value is the same key when it occurs often enough, else the smallest key above it
+// (one more min pass, only for CTAs that need it); the two are averaged (numpy.median / quantile(0.5) linear).
+// Any Z is accepted (the first version held a column in registers and stopped at Z = 1280).
 #include "common.cuh"
 
 #include <algorithm>
@@ -19,8 +24,8 @@
 namespace shrimpy {
 
 constexpr int kMedThreads = 256;
-constexpr int kMedTileX = 64;
-constexpr int kMedMaxPerLane = 40;   // Z <= 1280
+constexpr int kMedPixels = 64;                      // pixels per CTA
+constexpr int kMedQuarters = kMedThreads / kMedPixels;
 
 // order-preserving key: uint16 as is; float32 with the usual sign fix-up
 __device__ __forceinline__ uint32_t key_of(uint16_t v) { return v; }
@@ -34,80 +39,160 @@ template <> __device__ __forceinline__ float value_of<float>(uint32_t k) {
     return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
 }
 
-// k-th smallest (0-based) of the warp's keys; lanes hold `cnt` valid keys each in v[0..cnt)
-template <int NBITS, int MAXV>
-__device__ __forceinline__ uint32_t warp_select(const uint32_t (&v)[MAXV], int k) {
-    uint32_t prefix = 0;
-#pragma unroll 1
-    for (int bit = NBITS - 1; bit >= 0; --bit) {
-        // keys that match the decided prefix above `bit` and have this bit clear: (v & mask) == prefix, where
-        // mask covers `bit` and everything above it (prefix is still zero at `bit` and below; padding keys are
-        // all-ones and never match while a bit is undecided)
-        const uint32_t mask = 0xffffffffu << bit;
-        int c = 0;
-#pragma unroll
-        for (int i = 0; i < MAXV; ++i) c += ((v[i] & mask) == prefix) ? 1 : 0;
-        c = __reduce_add_sync(0xffffffffu, c);
-        if (k >= c) {
-            k -= c;
-            prefix |= 1u << bit;
-        }
-    }
-    return prefix;
-}
+template <typename T> struct Pair;
+template <> struct Pair<uint16_t> { typedef ushort2 type; };
+template <> struct Pair<float> { typedef float2 type; };
 
-template <typename T, int MAXV>   // MAXV = registers per lane holding column values: Z <= 32 * MAXV
+// PAIR: a thread loads two adjacent pixels with one 4 / 8 byte access (needs the alignment the host checks).
+// Per-pixel shared arrays are indexed by SLOT: pixel 2j lives in slot j, pixel 2j+1 in slot 32 + j, so that both
+// the counting phase (lane = pixel pair) and the search phase (lane = slot) touch 32 different banks per access.
+template <typename T, bool PAIR>
 __global__ void __launch_bounds__(kMedThreads) median_z_kernel(const T *__restrict__ raw, float *__restrict__ pattern,
-                                                               int Z, int Y, int X, long long sz, long long sy,
-                                                               int tiles_x, int tile_x, int pitch_elems) {
-    extern __shared__ __align__(16) unsigned char smem_med[];
-    T *tile = reinterpret_cast<T *>(smem_med);
-    const int y = blockIdx.x / tiles_x;
-    const int x0 = (blockIdx.x % tiles_x) * tile_x;
-    const int nx = min(tile_x, X - x0);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+                                                               int Z, int Y, int X, long long sz, long long sy, int tiles_x) {
+    extern __shared__ __align__(16) unsigned hist[];           // [256 bins][64 slots]
+    __shared__ unsigned part[kMedQuarters][kMedPixels];         // counts per quarter of the bins
+    __shared__ unsigned s_prefix[kMedPixels];                   // decided high bytes of the wanted key
+    __shared__ unsigned s_rank[kMedPixels];                     // rank still to be resolved among the matching keys
+    __shared__ unsigned s_le[kMedPixels];                       // keys <= the selected key (after the last pass)
+    __shared__ unsigned s_above[kMedPixels];                    // smallest key above the selected one (0 = not known yet)
 
-    // stage: one scan slice row (nx elements) per warp iteration, coalesced along x
-    for (int z = warp; z < Z; z += kMedThreads / 32) {
-        const T *src = raw + (long long)z * sz + (long long)y * sy + x0;
-        for (int i = lane; i < nx; i += 32) tile[z * pitch_elems + i] = __ldg(src + i);
+    constexpr int NB = sizeof(T);                               // key bytes: 2 or 4
+    constexpr int PPT = PAIR ? 2 : 1;                           // pixels per thread while counting
+    constexpr int kSlices = kMedThreads * PPT / kMedPixels;     // z slices the counting threads split the scan axis into
+    const int y = blockIdx.x / tiles_x;
+    const int x0 = (blockIdx.x % tiles_x) * kMedPixels;
+    const unsigned k_lo = (unsigned)(Z - 1) / 2, k_hi = (unsigned)Z / 2;   // the two middle ranks (equal for odd Z)
+
+    // counting role: pixel(s) cpx.. and z slice cq
+    const int cpx = PAIR ? 2 * (threadIdx.x % 32) : threadIdx.x % kMedPixels;
+    const int cq = PAIR ? threadIdx.x / 32 : threadIdx.x / kMedPixels;
+    const int cslot0 = PAIR ? threadIdx.x % 32 : (cpx >> 1) + 32 * (cpx & 1);
+    const bool clive0 = x0 + cpx < X, clive1 = PAIR && x0 + cpx + 1 < X;
+    const T *col = raw + (long long)y * sy + x0 + cpx;
+    // search role: slot sl (pixel spx), quarter q of the bins
+    const int sl = threadIdx.x % kMedPixels, q = threadIdx.x / kMedPixels;
+    const int spx = 2 * (sl % 32) + sl / 32;
+    const bool slive = x0 + spx < X;
+
+    for (int i = threadIdx.x; i < 256 * kMedPixels; i += kMedThreads) hist[i] = 0;
+    if (q == 0) {
+        s_prefix[sl] = 0;
+        s_rank[sl] = k_lo;
+        s_le[sl] = 0;
+        s_above[sl] = 0;
     }
     __syncthreads();
 
-    constexpr int NBITS = sizeof(T) == 2 ? 16 : 32;
-    const int k_hi = Z / 2, k_lo = (Z - 1) / 2;      // the two middle ranks (equal for odd Z)
-    for (int col = warp; col < nx; col += kMedThreads / 32) {
-        uint32_t v[MAXV];
-        int cnt = 0;
+#pragma unroll 1
+    for (int pass = 0; pass < NB; ++pass) {
+        const int shift = 8 * (NB - 1 - pass);
+        const unsigned prefix0 = s_prefix[cslot0], prefix1 = PAIR ? s_prefix[cslot0 + 32] : 0u;
+        auto count = [&](T v, unsigned prefix, int slot) {
+            const uint32_t key = key_of(v);
+            if (pass == 0 || (key >> (shift + 8)) == prefix) atomicAdd(&hist[((key >> shift) & 255u) * kMedPixels + slot], 1u);
+        };
+        if (clive0) {
+            // batches of independent loads keep enough bytes in flight (a plain loop was latency-bound)
+            constexpr int kBatch = 8;
+            int z = cq;
+            for (; z + (kBatch - 1) * kSlices < Z; z += kBatch * kSlices) {
+                if (PAIR) {
+                    typename Pair<T>::type v[kBatch];
 #pragma unroll
-        for (int i = 0; i < MAXV; ++i) {
-            const int z = lane + 32 * i;
-            v[i] = 0xffffffffu;
-            if (z < Z) {
-                v[i] = key_of(tile[z * pitch_elems + col]);
-                cnt = i + 1;
+                    for (int i = 0; i < kBatch; ++i)
+                        v[i] = __ldg(reinterpret_cast<const typename Pair<T>::type *>(col + (long long)(z + i * kSlices) * sz));
+#pragma unroll
+                    for (int i = 0; i < kBatch; ++i) {
+                        count(v[i].x, prefix0, cslot0);
+                        if (clive1) count(v[i].y, prefix1, cslot0 + 32);
+                    }
+                } else {
+                    T v[kBatch];
+#pragma unroll
+                    for (int i = 0; i < kBatch; ++i) v[i] = __ldg(col + (long long)(z + i * kSlices) * sz);
+#pragma unroll
+                    for (int i = 0; i < kBatch; ++i) count(v[i], prefix0, cslot0);
+                }
+            }
+            for (; z < Z; z += kSlices) {
+                count(__ldg(col + (long long)z * sz), prefix0, cslot0);
+                if (clive1) count(__ldg(col + (long long)z * sz + 1), prefix1, cslot0 + 32);
             }
         }
-        const uint32_t m_lo = warp_select<NBITS, MAXV>(v, k_lo);
-        float med = value_of<T>(m_lo);
-        if (k_hi != k_lo) {
-            // next order statistic: m_lo again if it occurs often enough, else the smallest key above it
-            int le = 0;
-            uint32_t above = 0xffffffffu;
-#pragma unroll
-            for (int i = 0; i < MAXV; ++i)
-                if (i < cnt) {
-                    le += v[i] <= m_lo ? 1 : 0;
-                    if (v[i] > m_lo) above = min(above, v[i]);
+        __syncthreads();
+        // four threads per pixel: counts of their 64 bins, then the quarter holding the rank scans again
+        unsigned mine = 0;
+        for (int b = 0; b < 64; ++b) mine += hist[(q * 64 + b) * kMedPixels + sl];
+        part[q][sl] = mine;
+        __syncthreads();
+        unsigned before = 0;
+        for (int i = 0; i < q; ++i) before += part[i][sl];
+        const unsigned rank = s_rank[sl], prefix = s_prefix[sl];
+        __syncthreads();                       // everyone has read s_rank / s_prefix before the owner rewrites them
+        if (rank >= before && rank < before + mine) {
+            unsigned acc = before;
+            int bin = q * 64;
+            for (;; ++bin) {
+                const unsigned c = hist[bin * kMedPixels + sl];
+                if (rank < acc + c) {
+                    s_prefix[sl] = (prefix << 8) | (unsigned)bin;
+                    s_rank[sl] = rank - acc;
+                    s_le[sl] += acc + (pass == NB - 1 ? c : 0u);   // keys below the bin (all passes) + the bin itself (last)
+                    break;
                 }
-            le = __reduce_add_sync(0xffffffffu, le);
-            above = __reduce_min_sync(0xffffffffu, above);
-            const uint32_t m_hi = (le > k_hi) ? m_lo : above;
-            // numpy: mean of the two middle values (float32 data stays float32)
-            med = (sizeof(T) == 2) ? 0.5f * (value_of<T>(m_lo) + value_of<T>(m_hi))
-                                   : __fmul_rn(__fadd_rn(value_of<T>(m_lo), value_of<T>(m_hi)), 0.5f);
+                acc += c;
+            }
+            if (pass == NB - 1 && k_hi != k_lo) {
+                // the smallest key above the selected one is the next occupied bin of this pass, if there is one
+                for (int nb = bin + 1; nb < 256; ++nb)
+                    if (hist[nb * kMedPixels + sl]) {
+                        s_above[sl] = ((prefix << 8) | (unsigned)nb) + 1u;   // stored + 1: 0 means "not found"
+                        break;
+                    }
+            }
         }
-        if (lane == 0) pattern[(long long)y * X + x0 + col] = med;
+        __syncthreads();
+        if (pass + 1 < NB) {
+            for (int i = threadIdx.x; i < 256 * kMedPixels; i += kMedThreads) hist[i] = 0;
+            __syncthreads();
+        }
+    }
+
+    if (k_hi != k_lo) {
+        // upper middle value: the same key if enough keys are <= it, else the smallest key above it; that one is
+        // known from the last histogram unless it differs in a higher byte -- then one min pass over the column
+        const bool need0 = clive0 && s_le[cslot0] <= k_hi && s_above[cslot0] == 0;
+        const bool need1 = clive1 && s_le[cslot0 + 32] <= k_hi && s_above[cslot0 + 32] == 0;
+        if (__syncthreads_or(need0 || need1)) {
+            if (q == 0 && s_above[sl] == 0) s_above[sl] = 0xffffffffu;
+            __syncthreads();
+            if (need0 || need1) {
+                const uint32_t m0 = s_prefix[cslot0], m1 = PAIR ? s_prefix[cslot0 + 32] : 0u;
+                uint32_t best0 = 0xffffffffu, best1 = 0xffffffffu;
+                for (int z = cq; z < Z; z += kSlices) {
+                    if (need0) {
+                        const uint32_t key = key_of(__ldg(col + (long long)z * sz));
+                        if (key > m0) best0 = min(best0, key);
+                    }
+                    if (need1) {
+                        const uint32_t key = key_of(__ldg(col + (long long)z * sz + 1));
+                        if (key > m1) best1 = min(best1, key);
+                    }
+                }
+                // stored + 1 like the histogram result (a key of 0xffffffff cannot be "above" anything that needs it)
+                if (need0 && best0 != 0xffffffffu) atomicMin(&s_above[cslot0], best0 + 1u);
+                if (need1 && best1 != 0xffffffffu) atomicMin(&s_above[cslot0 + 32], best1 + 1u);
+            }
+            __syncthreads();
+        }
+    }
+    if (q == 0 && slive) {
+        const uint32_t m_lo = s_prefix[sl];
+        const uint32_t m_hi = (k_hi == k_lo || s_le[sl] > k_hi) ? m_lo : s_above[sl] - 1u;
+        // numpy: mean of the two middle values (float32 data stays float32)
+        const float lo = value_of<T>(m_lo), hi = value_of<T>(m_hi);
+        const float med = (k_hi == k_lo) ? lo : (sizeof(T) == 2) ? 0.5f * (lo + hi) : __fmul_rn(__fadd_rn(lo, hi), 0.5f);
+        pattern[(long long)y * X + x0 + spx] = med;
     }
 }
 
@@ -152,40 +237,28 @@ extern "C" int shrimpy_flatfield_pattern_device(const void *d_raw, int raw_dtype
     if (Z <= 0 || Y <= 0 || X <= 0) return fail(SHRIMPY_EINVAL, "flatfield: bad shape (%d,%d,%d)", Z, Y, X);
     if (raw_dtype != SHRIMPY_U16 && raw_dtype != SHRIMPY_F32) return fail(SHRIMPY_EINVAL, "flatfield: bad dtype");
     if (!d_raw || !d_pattern) return fail(SHRIMPY_EINVAL, "flatfield: null device pointer");
-    if (Z > 32 * kMedMaxPerLane)
-        return fail(SHRIMPY_EINVAL, "flatfield: Z=%d exceeds the %d slices the median kernel holds in registers", Z,
-                    32 * kMedMaxPerLane);
     const long long sy = raw_stride_y ? raw_stride_y : X;
     const long long sz = raw_stride_z ? raw_stride_z : (long long)Y * sy;
-    const int es = raw_dtype == SHRIMPY_U16 ? 2 : 4;
-    // tile width: 64 pixels when the [Z][tile] slab fits shared memory (two CTAs per SM preferred), else narrower;
-    // row pitch: the tile plus one 4-byte bank so that a column walk hits distinct banks
-    int tile_x = kMedTileX;
-    while (tile_x > 16 && (size_t)Z * (tile_x + 4 / es) * es > 110 * 1024) tile_x >>= 1;
-    const int pitch_elems = tile_x + 4 / es;
-    const size_t smem = (size_t)Z * pitch_elems * es;
-    if (smem > 220 * 1024) return fail(SHRIMPY_EINVAL, "flatfield: Z=%d does not fit the shared-memory tile", Z);
-    const int tiles_x = (X + tile_x - 1) / tile_x;
+    const int tiles_x = (X + kMedPixels - 1) / kMedPixels;
     const long long blocks = (long long)tiles_x * Y;
     if (blocks > 2147483647LL) return fail(SHRIMPY_EINVAL, "flatfield: image too large for the grid");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    const int per_lane = (Z + 31) / 32;
-#define SHRIMPY_MEDIAN(T, V)                                                                                        \
-    do {                                                                                                            \
-        auto kern = median_z_kernel<T, V>;                                                                          \
-        if (smem + 1024 > 48 * 1024)                                                                                \
-            SHRIMPY_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
-        kern<<<(unsigned)blocks, kMedThreads, smem, s>>>(static_cast<const T *>(d_raw), d_pattern, Z, Y, X, sz, sy, \
-                                                          tiles_x, tile_x, pitch_elems);                             \
+    const size_t smem = 256 * kMedPixels * sizeof(unsigned);   // 64 KB of histograms: three CTAs per SM
+    const int es = raw_dtype == SHRIMPY_U16 ? 2 : 4;
+    // two pixels per load when every pair is naturally aligned: even strides, even X tile origin (always), aligned base
+    const bool pair = (reinterpret_cast<uintptr_t>(d_raw) % (2 * es)) == 0 && sy % 2 == 0 && sz % 2 == 0 && X % 2 == 0;
+#define SHRIMPY_MEDIAN(T, P)                                                                                         \
+    do {                                                                                                             \
+        auto kern = median_z_kernel<T, P>;                                                                           \
+        SHRIMPY_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));        \
+        kern<<<(unsigned)blocks, kMedThreads, smem, s>>>(static_cast<const T *>(d_raw), d_pattern, Z, Y, X, sz, sy, tiles_x); \
     } while (0)
     if (raw_dtype == SHRIMPY_U16) {
-        if (per_lane <= 8) SHRIMPY_MEDIAN(uint16_t, 8);
-        else if (per_lane <= 20) SHRIMPY_MEDIAN(uint16_t, 20);
-        else SHRIMPY_MEDIAN(uint16_t, kMedMaxPerLane);
+        if (pair) SHRIMPY_MEDIAN(uint16_t, true);
+        else SHRIMPY_MEDIAN(uint16_t, false);
     } else {
-        if (per_lane <= 8) SHRIMPY_MEDIAN(float, 8);
-        else if (per_lane <= 20) SHRIMPY_MEDIAN(float, 20);
-        else SHRIMPY_MEDIAN(float, kMedMaxPerLane);
+        if (pair) SHRIMPY_MEDIAN(float, true);
+        else SHRIMPY_MEDIAN(float, false);
     }
 #undef SHRIMPY_MEDIAN
     count_launch();

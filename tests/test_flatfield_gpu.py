@@ -43,7 +43,7 @@ def test_reference_golden(env):
             assert np.max(np.abs(got - want)) <= 2e-3, name
 
 
-@pytest.mark.parametrize("shape", [(8, 6, 10), (9, 5, 12), (33, 7, 64), (64, 3, 130), (600, 4, 192), (1201, 2, 70)])
+@pytest.mark.parametrize("shape", [(8, 6, 10), (9, 5, 12), (33, 7, 64), (64, 3, 130), (600, 4, 192), (1201, 2, 70), (2500, 2, 33)])
 @pytest.mark.parametrize("dtype", [np.uint16, np.float32])
 def test_median_pattern_is_exact(env, shape, dtype):
     """The radix select is exact: the pattern equals numpy.median bit for bit (even and odd Z, ties included)."""
