@@ -15,7 +15,7 @@
 // uint16 needs 2 passes, float32 4; the slab of a CTA (Z x 64 pixels) is re-read from L1/L2, DRAM sees it once.
 // For even Z the upper middle value is the same key when it occurs often enough, else the smallest key above it
 // (one more min pass, only for CTAs that need it); the two are averaged (numpy.median / quantile(0.5) linear).
-// Any Z is accepted (the first version held a column in registers and stopped at Z = 1280).
+// Z up to 65535 (the first version held a column in registers and stopped at Z = 1280).
 #include "common.cuh"
 
 #include <algorithm>
@@ -44,17 +44,19 @@ template <> struct Pair<uint16_t> { typedef ushort2 type; };
 template <> struct Pair<float> { typedef float2 type; };
 
 // PAIR: a thread loads two adjacent pixels with one 4 / 8 byte access (needs the alignment the host checks).
-// Per-pixel shared arrays are indexed by SLOT: pixel 2j lives in slot j, pixel 2j+1 in slot 32 + j, so that both
-// the counting phase (lane = pixel pair) and the search phase (lane = slot) touch 32 different banks per access.
+// Histogram counters are 16 bits wide (Z <= 65535), two pixels per 32-bit word -- pixel 2j in the low half of word j,
+// pixel 2j+1 in the high half -- so the 256 x 64 counters take 32 KB and six CTAs fit an SM (the kernel is latency-
+// bound: more resident warps is what it needs).  A warp's 32 pixel pairs hit 32 different words per access.
 template <typename T, bool PAIR>
 __global__ void __launch_bounds__(kMedThreads) median_z_kernel(const T *__restrict__ raw, float *__restrict__ pattern,
                                                                int Z, int Y, int X, long long sz, long long sy, int tiles_x) {
-    extern __shared__ __align__(16) unsigned hist[];           // [256 bins][64 slots]
+    constexpr int kWords = kMedPixels / 2;
+    extern __shared__ __align__(16) unsigned hist[];           // [256 bins][32 words], two 16-bit counters per word
     __shared__ unsigned part[kMedQuarters][kMedPixels];         // counts per quarter of the bins
     __shared__ unsigned s_prefix[kMedPixels];                   // decided high bytes of the wanted key
     __shared__ unsigned s_rank[kMedPixels];                     // rank still to be resolved among the matching keys
     __shared__ unsigned s_le[kMedPixels];                       // keys <= the selected key (after the last pass)
-    __shared__ unsigned s_above[kMedPixels];                    // smallest key above the selected one (0 = not known yet)
+    __shared__ unsigned s_above[kMedPixels];                    // smallest key above the selected one, + 1 (0 = not known yet)
 
     constexpr int NB = sizeof(T);                               // key bytes: 2 or 4
     constexpr int PPT = PAIR ? 2 : 1;                           // pixels per thread while counting
@@ -63,33 +65,33 @@ __global__ void __launch_bounds__(kMedThreads) median_z_kernel(const T *__restri
     const int x0 = (blockIdx.x % tiles_x) * kMedPixels;
     const unsigned k_lo = (unsigned)(Z - 1) / 2, k_hi = (unsigned)Z / 2;   // the two middle ranks (equal for odd Z)
 
-    // counting role: pixel(s) cpx.. and z slice cq
-    const int cpx = PAIR ? 2 * (threadIdx.x % 32) : threadIdx.x % kMedPixels;
-    const int cq = PAIR ? threadIdx.x / 32 : threadIdx.x / kMedPixels;
-    const int cslot0 = PAIR ? threadIdx.x % 32 : (cpx >> 1) + 32 * (cpx & 1);
+    // counting role: pixel(s) cpx (and cpx + 1), z slice cq
+    const int cpx = PAIR ? 2 * (threadIdx.x % kWords) : threadIdx.x % kMedPixels;
+    const int cq = PAIR ? threadIdx.x / kWords : threadIdx.x / kMedPixels;
     const bool clive0 = x0 + cpx < X, clive1 = PAIR && x0 + cpx + 1 < X;
     const T *col = raw + (long long)y * sy + x0 + cpx;
-    // search role: slot sl (pixel spx), quarter q of the bins
-    const int sl = threadIdx.x % kMedPixels, q = threadIdx.x / kMedPixels;
-    const int spx = 2 * (sl % 32) + sl / 32;
+    // search role: pixel spx, quarter q of the bins
+    const int spx = threadIdx.x % kMedPixels, q = threadIdx.x / kMedPixels;
+    const int sword = spx >> 1, sshift = 16 * (spx & 1);
     const bool slive = x0 + spx < X;
 
-    for (int i = threadIdx.x; i < 256 * kMedPixels; i += kMedThreads) hist[i] = 0;
+    for (int i = threadIdx.x; i < 256 * kWords; i += kMedThreads) hist[i] = 0;
     if (q == 0) {
-        s_prefix[sl] = 0;
-        s_rank[sl] = k_lo;
-        s_le[sl] = 0;
-        s_above[sl] = 0;
+        s_prefix[spx] = 0;
+        s_rank[spx] = k_lo;
+        s_le[spx] = 0;
+        s_above[spx] = 0;
     }
     __syncthreads();
 
 #pragma unroll 1
     for (int pass = 0; pass < NB; ++pass) {
         const int shift = 8 * (NB - 1 - pass);
-        const unsigned prefix0 = s_prefix[cslot0], prefix1 = PAIR ? s_prefix[cslot0 + 32] : 0u;
-        auto count = [&](T v, unsigned prefix, int slot) {
+        const unsigned prefix0 = s_prefix[cpx], prefix1 = PAIR ? s_prefix[cpx + 1] : 0u;
+        auto count = [&](T v, unsigned prefix, int px) {
             const uint32_t key = key_of(v);
-            if (pass == 0 || (key >> (shift + 8)) == prefix) atomicAdd(&hist[((key >> shift) & 255u) * kMedPixels + slot], 1u);
+            if (pass == 0 || (key >> (shift + 8)) == prefix)
+                atomicAdd(&hist[((key >> shift) & 255u) * kWords + (px >> 1)], 1u << (16 * (px & 1)));
         };
         if (clive0) {
             // batches of independent loads keep enough bytes in flight (a plain loop was latency-bound)
@@ -103,41 +105,41 @@ __global__ void __launch_bounds__(kMedThreads) median_z_kernel(const T *__restri
                         v[i] = __ldg(reinterpret_cast<const typename Pair<T>::type *>(col + (long long)(z + i * kSlices) * sz));
 #pragma unroll
                     for (int i = 0; i < kBatch; ++i) {
-                        count(v[i].x, prefix0, cslot0);
-                        if (clive1) count(v[i].y, prefix1, cslot0 + 32);
+                        count(v[i].x, prefix0, cpx);
+                        if (clive1) count(v[i].y, prefix1, cpx + 1);
                     }
                 } else {
                     T v[kBatch];
 #pragma unroll
                     for (int i = 0; i < kBatch; ++i) v[i] = __ldg(col + (long long)(z + i * kSlices) * sz);
 #pragma unroll
-                    for (int i = 0; i < kBatch; ++i) count(v[i], prefix0, cslot0);
+                    for (int i = 0; i < kBatch; ++i) count(v[i], prefix0, cpx);
                 }
             }
             for (; z < Z; z += kSlices) {
-                count(__ldg(col + (long long)z * sz), prefix0, cslot0);
-                if (clive1) count(__ldg(col + (long long)z * sz + 1), prefix1, cslot0 + 32);
+                count(__ldg(col + (long long)z * sz), prefix0, cpx);
+                if (clive1) count(__ldg(col + (long long)z * sz + 1), prefix1, cpx + 1);
             }
         }
         __syncthreads();
         // four threads per pixel: counts of their 64 bins, then the quarter holding the rank scans again
         unsigned mine = 0;
-        for (int b = 0; b < 64; ++b) mine += hist[(q * 64 + b) * kMedPixels + sl];
-        part[q][sl] = mine;
+        for (int b = 0; b < 64; ++b) mine += (hist[(q * 64 + b) * kWords + sword] >> sshift) & 0xffffu;
+        part[q][spx] = mine;
         __syncthreads();
         unsigned before = 0;
-        for (int i = 0; i < q; ++i) before += part[i][sl];
-        const unsigned rank = s_rank[sl], prefix = s_prefix[sl];
+        for (int i = 0; i < q; ++i) before += part[i][spx];
+        const unsigned rank = s_rank[spx], prefix = s_prefix[spx];
         __syncthreads();                       // everyone has read s_rank / s_prefix before the owner rewrites them
         if (rank >= before && rank < before + mine) {
             unsigned acc = before;
             int bin = q * 64;
             for (;; ++bin) {
-                const unsigned c = hist[bin * kMedPixels + sl];
+                const unsigned c = (hist[bin * kWords + sword] >> sshift) & 0xffffu;
                 if (rank < acc + c) {
-                    s_prefix[sl] = (prefix << 8) | (unsigned)bin;
-                    s_rank[sl] = rank - acc;
-                    s_le[sl] += acc + (pass == NB - 1 ? c : 0u);   // keys below the bin (all passes) + the bin itself (last)
+                    s_prefix[spx] = (prefix << 8) | (unsigned)bin;
+                    s_rank[spx] = rank - acc;
+                    s_le[spx] += acc + (pass == NB - 1 ? c : 0u);   // keys below the bin (all passes) + the bin itself (last)
                     break;
                 }
                 acc += c;
@@ -145,15 +147,15 @@ __global__ void __launch_bounds__(kMedThreads) median_z_kernel(const T *__restri
             if (pass == NB - 1 && k_hi != k_lo) {
                 // the smallest key above the selected one is the next occupied bin of this pass, if there is one
                 for (int nb = bin + 1; nb < 256; ++nb)
-                    if (hist[nb * kMedPixels + sl]) {
-                        s_above[sl] = ((prefix << 8) | (unsigned)nb) + 1u;   // stored + 1: 0 means "not found"
+                    if ((hist[nb * kWords + sword] >> sshift) & 0xffffu) {
+                        s_above[spx] = ((prefix << 8) | (unsigned)nb) + 1u;
                         break;
                     }
             }
         }
         __syncthreads();
         if (pass + 1 < NB) {
-            for (int i = threadIdx.x; i < 256 * kMedPixels; i += kMedThreads) hist[i] = 0;
+            for (int i = threadIdx.x; i < 256 * kWords; i += kMedThreads) hist[i] = 0;
             __syncthreads();
         }
     }
@@ -161,13 +163,13 @@ __global__ void __launch_bounds__(kMedThreads) median_z_kernel(const T *__restri
     if (k_hi != k_lo) {
         // upper middle value: the same key if enough keys are <= it, else the smallest key above it; that one is
         // known from the last histogram unless it differs in a higher byte -- then one min pass over the column
-        const bool need0 = clive0 && s_le[cslot0] <= k_hi && s_above[cslot0] == 0;
-        const bool need1 = clive1 && s_le[cslot0 + 32] <= k_hi && s_above[cslot0 + 32] == 0;
+        const bool need0 = clive0 && s_le[cpx] <= k_hi && s_above[cpx] == 0;
+        const bool need1 = clive1 && s_le[cpx + 1] <= k_hi && s_above[cpx + 1] == 0;
         if (__syncthreads_or(need0 || need1)) {
-            if (q == 0 && s_above[sl] == 0) s_above[sl] = 0xffffffffu;
+            if (q == 0 && s_above[spx] == 0) s_above[spx] = 0xffffffffu;
             __syncthreads();
             if (need0 || need1) {
-                const uint32_t m0 = s_prefix[cslot0], m1 = PAIR ? s_prefix[cslot0 + 32] : 0u;
+                const uint32_t m0 = s_prefix[cpx], m1 = PAIR ? s_prefix[cpx + 1] : 0u;
                 uint32_t best0 = 0xffffffffu, best1 = 0xffffffffu;
                 for (int z = cq; z < Z; z += kSlices) {
                     if (need0) {
@@ -179,16 +181,16 @@ __global__ void __launch_bounds__(kMedThreads) median_z_kernel(const T *__restri
                         if (key > m1) best1 = min(best1, key);
                     }
                 }
-                // stored + 1 like the histogram result (a key of 0xffffffff cannot be "above" anything that needs it)
-                if (need0 && best0 != 0xffffffffu) atomicMin(&s_above[cslot0], best0 + 1u);
-                if (need1 && best1 != 0xffffffffu) atomicMin(&s_above[cslot0 + 32], best1 + 1u);
+                // stored + 1 like the histogram result
+                if (need0 && best0 != 0xffffffffu) atomicMin(&s_above[cpx], best0 + 1u);
+                if (need1 && best1 != 0xffffffffu) atomicMin(&s_above[cpx + 1], best1 + 1u);
             }
             __syncthreads();
         }
     }
     if (q == 0 && slive) {
-        const uint32_t m_lo = s_prefix[sl];
-        const uint32_t m_hi = (k_hi == k_lo || s_le[sl] > k_hi) ? m_lo : s_above[sl] - 1u;
+        const uint32_t m_lo = s_prefix[spx];
+        const uint32_t m_hi = (k_hi == k_lo || s_le[spx] > k_hi) ? m_lo : s_above[spx] - 1u;
         // numpy: mean of the two middle values (float32 data stays float32)
         const float lo = value_of<T>(m_lo), hi = value_of<T>(m_hi);
         const float med = (k_hi == k_lo) ? lo : (sizeof(T) == 2) ? 0.5f * (lo + hi) : __fmul_rn(__fadd_rn(lo, hi), 0.5f);
@@ -220,12 +222,39 @@ __global__ void __launch_bounds__(256) pattern_scale_kernel(const float *__restr
         scale[i] = mean / pattern[i];
 }
 
-// standalone correction (when the deskew does not follow): out = raw * scale[y,x], float32
-template <typename T>
+// standalone correction (when the deskew does not follow): out = raw * scale[y,x], float32.
+// A thread owns VEC consecutive pixels (16 bytes of input) and walks a range of slices, so the scale values are read
+// once per thread and every access is a full 16-byte vector; VEC = 1 is the unaligned fallback.
+template <typename T, int VEC>
 __global__ void __launch_bounds__(256) apply_scale_kernel(const T *__restrict__ raw, const float *__restrict__ scale,
-                                                          float *__restrict__ out, long long plane, long long total) {
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
-        __stcs(out + i, (float)__ldg(raw + i) * __ldg(scale + i % plane));
+                                                          float *__restrict__ out, long long plane, int Z, int z_per_block) {
+    const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * VEC;
+    if (i >= plane) return;
+    const int z0 = blockIdx.y * z_per_block, z1 = min(Z, z0 + z_per_block);
+    float g[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) g[j] = __ldg(scale + i + j);
+    for (int z = z0; z < z1; ++z) {
+        const T *src = raw + (long long)z * plane + i;
+        float *dst = out + (long long)z * plane + i;
+        if (VEC == 1) {
+            __stcs(dst, (float)__ldg(src) * g[0]);
+        } else if (sizeof(T) == 2) {   // VEC == 8: one uint4 in, two float4 out
+            const uint4 v = __ldg(reinterpret_cast<const uint4 *>(src));
+            const unsigned w[4] = {v.x, v.y, v.z, v.w};
+            float r[8];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                r[2 * j] = (float)(w[j] & 0xffffu) * g[2 * j];
+                r[2 * j + 1] = (float)(w[j] >> 16) * g[2 * j + 1];
+            }
+            __stcs(reinterpret_cast<float4 *>(dst), make_float4(r[0], r[1], r[2], r[3]));
+            __stcs(reinterpret_cast<float4 *>(dst) + 1, make_float4(r[4], r[5], r[6], r[7]));
+        } else {                       // VEC == 4: one float4 in, one float4 out
+            const float4 v = __ldg(reinterpret_cast<const float4 *>(src));
+            __stcs(reinterpret_cast<float4 *>(dst), make_float4(v.x * g[0], v.y * g[1], v.z * g[2], v.w * g[3]));
+        }
+    }
 }
 
 }  // namespace shrimpy
@@ -243,7 +272,8 @@ extern "C" int shrimpy_flatfield_pattern_device(const void *d_raw, int raw_dtype
     const long long blocks = (long long)tiles_x * Y;
     if (blocks > 2147483647LL) return fail(SHRIMPY_EINVAL, "flatfield: image too large for the grid");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    const size_t smem = 256 * kMedPixels * sizeof(unsigned);   // 64 KB of histograms: three CTAs per SM
+    if (Z > 65535) return fail(SHRIMPY_EINVAL, "flatfield: Z=%d exceeds the 16-bit histogram counters", Z);
+    const size_t smem = 256 * (kMedPixels / 2) * sizeof(unsigned);   // 32 KB of packed histograms: six CTAs per SM
     const int es = raw_dtype == SHRIMPY_U16 ? 2 : 4;
     // two pixels per load when every pair is naturally aligned: even strides, even X tile origin (always), aligned base
     const bool pair = (reinterpret_cast<uintptr_t>(d_raw) % (2 * es)) == 0 && sy % 2 == 0 && sz % 2 == 0 && X % 2 == 0;
@@ -283,13 +313,27 @@ extern "C" int shrimpy_flatfield_apply_device(const void *d_raw, int raw_dtype, 
                                               int Y, int X, void *stream) {
     if (Z <= 0 || Y <= 0 || X <= 0 || !d_raw || !d_scale || !d_out) return fail(SHRIMPY_EINVAL, "flatfield apply: bad arguments");
     if (raw_dtype != SHRIMPY_U16 && raw_dtype != SHRIMPY_F32) return fail(SHRIMPY_EINVAL, "flatfield apply: bad dtype");
-    const long long plane = (long long)Y * X, total = plane * Z;
-    const int blocks = (int)std::min<long long>((total + 255) / 256, 148LL * 32);
+    const long long plane = (long long)Y * X;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    if (raw_dtype == SHRIMPY_U16)
-        apply_scale_kernel<uint16_t><<<blocks, 256, 0, s>>>(static_cast<const uint16_t *>(d_raw), d_scale, d_out, plane, total);
-    else
-        apply_scale_kernel<float><<<blocks, 256, 0, s>>>(static_cast<const float *>(d_raw), d_scale, d_out, plane, total);
+    const int vec = raw_dtype == SHRIMPY_U16 ? 8 : 4;
+    const bool aligned = plane % vec == 0 && (reinterpret_cast<uintptr_t>(d_raw) & 15u) == 0 &&
+                         (reinterpret_cast<uintptr_t>(d_out) & 15u) == 0 && (reinterpret_cast<uintptr_t>(d_scale) & 15u) == 0;
+    const int v = aligned ? vec : 1;
+    const long long threads = (plane + v - 1) / v;
+    const long long bx = (threads + 255) / 256;
+    // enough CTAs to fill the machine a few times over: split the scan axis when the image alone is too small
+    int zsplit = (int)std::min<long long>(Z, std::max<long long>(1, (148LL * 16 + bx - 1) / bx));
+    const int z_per_block = (Z + zsplit - 1) / zsplit;
+    zsplit = (Z + z_per_block - 1) / z_per_block;
+    if (bx > 2147483647LL || zsplit > 65535) return fail(SHRIMPY_EINVAL, "flatfield apply: image too large for the grid");
+    const dim3 grid((unsigned)bx, (unsigned)zsplit);
+    if (raw_dtype == SHRIMPY_U16) {
+        if (aligned) apply_scale_kernel<uint16_t, 8><<<grid, 256, 0, s>>>(static_cast<const uint16_t *>(d_raw), d_scale, d_out, plane, Z, z_per_block);
+        else apply_scale_kernel<uint16_t, 1><<<grid, 256, 0, s>>>(static_cast<const uint16_t *>(d_raw), d_scale, d_out, plane, Z, z_per_block);
+    } else {
+        if (aligned) apply_scale_kernel<float, 4><<<grid, 256, 0, s>>>(static_cast<const float *>(d_raw), d_scale, d_out, plane, Z, z_per_block);
+        else apply_scale_kernel<float, 1><<<grid, 256, 0, s>>>(static_cast<const float *>(d_raw), d_scale, d_out, plane, Z, z_per_block);
+    }
     count_launch();
     SHRIMPY_CUDA_TRY(cudaGetLastError());
     return SHRIMPY_OK;
