@@ -143,6 +143,17 @@ int shrimpy_deskew_flatfield_device(const void *d_raw, int raw_dtype, const floa
                                     int kernel, void *stream);
 
 /*
+ * Deskew with the value range of the result reduced in the same pass (fused epilogue): d_range2 receives
+ * (min, max) over every voxel written, padding included -- what torch.min / torch.max of the deskewed volume
+ * return in the tracking step that follows the deskew (shrimpy/dynatrack/tracking.py:583-584), so that the
+ * histogram pass of shrimpy_hist256_device can start without a pass of its own.  d_scale may be NULL (no
+ * flat-field).  Full stack only (no window); asynchronous like every device call.
+ */
+int shrimpy_deskew_range_device(const void *d_raw, int raw_dtype, const float *d_scale, float *d_out, float *d_range2,
+                                int Z, int Y, int X, int Xp, int n_avg, double m00, double m02, double shift,
+                                float cval, int64_t raw_stride_z, int64_t raw_stride_y, int kernel, void *stream);
+
+/*
  * Device-resident trilinear resample with a 3x4 (row-major, 12 doubles)
  * output-index -> input-index matrix in ZYX voxel units (the registration
  * resample named by BASELINE.json configs[2]; upstream

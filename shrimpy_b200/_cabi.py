@@ -31,6 +31,7 @@ EXPORTS = (
     "shrimpy_flatfield_scale_device",
     "shrimpy_flatfield_apply_device",
     "shrimpy_deskew_flatfield_device",
+    "shrimpy_deskew_range_device",
     "shrimpy_affine_device",
     "shrimpy_minmax_device",
     "shrimpy_hist256_device",
@@ -96,6 +97,9 @@ def _declare(lib) -> None:
     lib.shrimpy_deskew_flatfield_device.argtypes = [c_vp, c_int, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int,
                                                     c_dbl, c_dbl, c_dbl, c_flt, c_i64, c_i64,
                                                     ctypes.POINTER(Window), c_int, c_vp]
+    lib.shrimpy_deskew_range_device.restype = c_int
+    lib.shrimpy_deskew_range_device.argtypes = [c_vp, c_int, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int,
+                                                c_dbl, c_dbl, c_dbl, c_flt, c_i64, c_i64, c_int, c_vp]
     lib.shrimpy_affine_device.restype = c_int
     lib.shrimpy_affine_device.argtypes = [c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int,
                                           ctypes.POINTER(c_dbl), c_flt, c_int, c_vp]

@@ -148,6 +148,15 @@ __device__ __forceinline__ void tma_load_3d(uint32_t smem_dst, const CUtensorMap
         : "memory");
 }
 
+// Order-preserving float <-> uint map: atomicMin / atomicMax on unsigned words work for any sign.
+__device__ __forceinline__ unsigned ordered_key(float f) {
+    const unsigned u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ordered_value(unsigned k) {
+    return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
 #endif  // __CUDACC__
 
 }  // namespace shrimpy

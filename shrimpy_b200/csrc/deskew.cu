@@ -40,6 +40,7 @@ struct DeskewParams {
     float cval;
     float inv_n;
     const float *scale;  // optional flat-field scale field (Y, X) of the FULL stack, or nullptr
+    unsigned *range;     // optional: ordered keys of (min, max) over every voxel written (fused value range), or nullptr
     int T2;        // o2 extent of a tile (32, 64, 128 or 256)
     int nz_cap;    // scan slices per staged row (multiple of 8, <= 256)
     int tiles_x;   // number of raw-x tiles
@@ -103,6 +104,10 @@ __global__ void __launch_bounds__(128) deskew_direct_kernel(const DeskewParams P
     }
     const float r = (n_in == 0) ? P.cval : P.scale ? G : (P.n == 1) ? one : fmaf(S, P.inv_n, W);
     __stcs(P.out + (long long)(p - P.p0) * P.out_sp + (long long)o1 * P.out_s1 + (o2 - P.cbeg), r);
+    if (P.range) {   // fallback path of the fused value range: one atomic pair per active thread
+        atomicMin(P.range, ordered_key(r));
+        atomicMax(P.range + 1, ordered_key(r));
+    }
 }
 
 // ---- TMA-staged kernel -------------------------------------------------------
@@ -230,7 +235,10 @@ constexpr int kTmaThreads = 256;
 constexpr int kRowBytes = 128;  // one staged row = 128 B of raw x = one swizzle span
 constexpr int kMaxTmaAvg = 4;   // template instantiations exist for n = 1..4
 
-template <typename T, int NAVG, bool SCALED>
+// RANGE: the value range of the written voxels is reduced in the same pass (per thread -> warp shuffle -> CTA ->
+// one atomicMin / atomicMax pair per CTA on ordered keys): the min/max pass the tracking step makes right after
+// the deskew (shrimpy/dynatrack/tracking.py:583-584) disappears.
+template <typename T, int NAVG, bool SCALED, bool RANGE>
 __global__ void __launch_bounds__(kTmaThreads, 4)
     deskew_tma_kernel(const __grid_constant__ CUtensorMap tmap, const DeskewParams P) {
     constexpr int EPC = Chunk<T>::kElems;
@@ -340,6 +348,7 @@ __global__ void __launch_bounds__(kTmaThreads, 4)
 
     char *out_col = reinterpret_cast<char *>(P.out + (long long)(p - P.p0) * P.out_sp + (o2 - P.cbeg));
     const long long row_bytes = P.out_s1 * (long long)sizeof(float);
+    float vlo = 3.402823466e38f, vhi = -3.402823466e38f;
 
     for (int c = part; c < 8; c += parts) {
         float r[EPC];
@@ -387,16 +396,61 @@ __global__ void __launch_bounds__(kTmaThreads, 4)
                     __stcs(reinterpret_cast<float *>(ptr), r[j]);   // streaming: outputs are never re-read
                     ptr -= row_bytes;
                     asm volatile("" : "+l"(ptr));  // keep a stepped pointer (2 adds), not base+offset (4)
+                    if (RANGE) {
+                        vlo = fminf(vlo, r[j]);
+                        vhi = fmaxf(vhi, r[j]);
+                    }
                 }
             } else {
 #pragma unroll
                 for (int j = 0; j < EPC; ++j) {
-                    if (j < xvalid) __stcs(reinterpret_cast<float *>(ptr), r[j]);
+                    if (j < xvalid) {
+                        __stcs(reinterpret_cast<float *>(ptr), r[j]);
+                        if (RANGE) {
+                            vlo = fminf(vlo, r[j]);
+                            vhi = fmaxf(vhi, r[j]);
+                        }
+                    }
                     ptr -= row_bytes;
                 }
             }
         }
     }
+    if (RANGE) {
+        __shared__ float s_lo[kTmaThreads / 32], s_hi[kTmaThreads / 32];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            vlo = fminf(vlo, __shfl_xor_sync(0xffffffffu, vlo, o));
+            vhi = fmaxf(vhi, __shfl_xor_sync(0xffffffffu, vhi, o));
+        }
+        if (lane == 0) {
+            s_lo[warp] = vlo;
+            s_hi[warp] = vhi;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+#pragma unroll
+            for (int i = 1; i < kTmaThreads / 32; ++i) {
+                vlo = fminf(vlo, s_lo[i]);
+                vhi = fmaxf(vhi, s_hi[i]);
+            }
+            if (vlo <= vhi) {   // the CTA wrote something
+                atomicMin(P.range, ordered_key(vlo));
+                atomicMax(P.range + 1, ordered_key(vhi));
+            }
+        }
+    }
+}
+
+__global__ void range_init_kernel(unsigned *slots) {
+    slots[0] = 0xffffffffu;
+    slots[1] = 0u;
+}
+
+__global__ void range_finish_kernel(unsigned *slots) {
+    const float lo = ordered_value(slots[0]), hi = ordered_value(slots[1]);
+    reinterpret_cast<float *>(slots)[0] = lo;
+    reinterpret_cast<float *>(slots)[1] = hi;
 }
 
 // ---- host side -----------------------------------------------------------------
@@ -422,7 +476,8 @@ static int launch_direct(const DeskewParams &Pin, cudaStream_t stream) {
 
 template <typename T, int NAVG>
 static int launch_tma_n(const CUtensorMap &tmap, const DeskewParams &P, size_t smem, cudaStream_t stream) {
-    auto kern = P.scale ? deskew_tma_kernel<T, NAVG, true> : deskew_tma_kernel<T, NAVG, false>;
+    auto kern = P.scale ? (P.range ? deskew_tma_kernel<T, NAVG, true, true> : deskew_tma_kernel<T, NAVG, true, false>)
+                        : (P.range ? deskew_tma_kernel<T, NAVG, false, true> : deskew_tma_kernel<T, NAVG, false, false>);
     if (smem + 1024 > 48 * 1024)  // static smem counts against the 48 KB default as well
         SHRIMPY_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<dim3((unsigned)((long long)P.tiles_x * P.tiles_o2), (unsigned)P.pcount), kTmaThreads, smem, stream>>>(tmap, P);
@@ -562,7 +617,7 @@ extern "C" int shrimpy_deskew_window_needs(int Z, int Y, int n_avg, double m00, 
 static int deskew_window_impl(const void *d_raw, int raw_dtype, float *d_out, int Z, int Y, int X, int Xp, int n_avg,
                               double m00, double m02, double shift, float cval, int64_t raw_stride_z,
                               int64_t raw_stride_y, int64_t out_stride_p, int64_t out_stride_1,
-                              const shrimpy_window *win, const float *d_scale, int kernel, void *stream) {
+                              const shrimpy_window *win, const float *d_scale, float *d_range, int kernel, void *stream) {
     if (Z <= 0 || Y <= 0 || X <= 0 || Xp < 0 || n_avg <= 0)
         return fail(SHRIMPY_EINVAL, "deskew: bad shape Z=%d Y=%d X=%d Xp=%d n=%d", Z, Y, X, Xp, n_avg);
     if (raw_dtype != SHRIMPY_U16 && raw_dtype != SHRIMPY_F32)
@@ -608,8 +663,19 @@ static int deskew_window_impl(const void *d_raw, int raw_dtype, float *d_out, in
     P.cval = cval;
     P.inv_n = 1.0f / (float)n_avg;
     P.scale = d_scale;
+    P.range = reinterpret_cast<unsigned *>(d_range);   // the two result floats double as the ordered-key slots
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    return raw_dtype == SHRIMPY_U16 ? deskew_dispatch<uint16_t>(P, kernel, s) : deskew_dispatch<float>(P, kernel, s);
+    if (d_range) {
+        range_init_kernel<<<1, 1, 0, s>>>(P.range);
+        count_launch();
+    }
+    const int err = raw_dtype == SHRIMPY_U16 ? deskew_dispatch<uint16_t>(P, kernel, s) : deskew_dispatch<float>(P, kernel, s);
+    if (err == SHRIMPY_OK && d_range) {
+        range_finish_kernel<<<1, 1, 0, s>>>(P.range);
+        count_launch();
+        SHRIMPY_CUDA_TRY(cudaGetLastError());
+    }
+    return err;
 }
 
 extern "C" int shrimpy_deskew_window_device(const void *d_raw, int raw_dtype, float *d_out, int Z, int Y, int X,
@@ -618,7 +684,7 @@ extern "C" int shrimpy_deskew_window_device(const void *d_raw, int raw_dtype, fl
                                             int64_t out_stride_1, const shrimpy_window *win, int kernel,
                                             void *stream) {
     return deskew_window_impl(d_raw, raw_dtype, d_out, Z, Y, X, Xp, n_avg, m00, m02, shift, cval, raw_stride_z,
-                              raw_stride_y, out_stride_p, out_stride_1, win, nullptr, kernel, stream);
+                              raw_stride_y, out_stride_p, out_stride_1, win, nullptr, nullptr, kernel, stream);
 }
 
 extern "C" int shrimpy_deskew_flatfield_device(const void *d_raw, int raw_dtype, const float *d_scale, float *d_out,
@@ -627,7 +693,16 @@ extern "C" int shrimpy_deskew_flatfield_device(const void *d_raw, int raw_dtype,
                                                const shrimpy_window *win, int kernel, void *stream) {
     if (!d_scale) return fail(SHRIMPY_EINVAL, "deskew: null flat-field scale field");
     return deskew_window_impl(d_raw, raw_dtype, d_out, Z, Y, X, Xp, n_avg, m00, m02, shift, cval, raw_stride_z,
-                              raw_stride_y, 0, 0, win, d_scale, kernel, stream);
+                              raw_stride_y, 0, 0, win, d_scale, nullptr, kernel, stream);
+}
+
+extern "C" int shrimpy_deskew_range_device(const void *d_raw, int raw_dtype, const float *d_scale, float *d_out,
+                                           float *d_range2, int Z, int Y, int X, int Xp, int n_avg, double m00,
+                                           double m02, double shift, float cval, int64_t raw_stride_z,
+                                           int64_t raw_stride_y, int kernel, void *stream) {
+    if (!d_range2) return fail(SHRIMPY_EINVAL, "deskew: null value-range pointer");
+    return deskew_window_impl(d_raw, raw_dtype, d_out, Z, Y, X, Xp, n_avg, m00, m02, shift, cval, raw_stride_z,
+                              raw_stride_y, 0, 0, nullptr, d_scale, d_range2, kernel, stream);
 }
 
 extern "C" int shrimpy_deskew_device(const void *d_raw, int raw_dtype, float *d_out, int Z, int Y, int X, int Xp,

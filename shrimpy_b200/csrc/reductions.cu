@@ -11,14 +11,6 @@
 
 namespace shrimpy {
 
-__device__ __forceinline__ unsigned ordered_key(float f) {
-    const unsigned u = __float_as_uint(f);
-    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
-}
-__device__ __forceinline__ float ordered_value(unsigned k) {
-    return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
-}
-
 __global__ void minmax_init_kernel(unsigned *slots) {
     slots[0] = 0xffffffffu;
     slots[1] = 0u;

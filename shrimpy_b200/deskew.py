@@ -151,11 +151,16 @@ def _resolve_cval(torch, raw, code, cval, stream) -> float:
 
 
 def deskew_zyx(raw_data, ls_angle_deg: float, px_to_scan_ratio: float, keep_overhang: bool,
-               average_n_slices: int = 1, cval: Optional[float] = 0.0, out=None, kernel: str = "auto"):
+               average_n_slices: int = 1, cval: Optional[float] = 0.0, out=None, kernel: str = "auto",
+               value_range=None, scale=None):
     """Deskew a CUDA tensor ``(Z, Y, X)`` (uint16 or float32) into float32 ``(ceil(Y/n), X, Xp)``.
 
     Runs asynchronously on torch's current stream; ``out`` may be a preallocated
-    contiguous float32 tensor of the deskewed shape.
+    contiguous float32 tensor of the deskewed shape.  ``value_range``: an optional float32 CUDA tensor
+    of two elements that receives ``(min, max)`` of the deskewed volume, reduced inside the deskew
+    kernel (the range the tracking step needs next, ``shrimpy/dynatrack/tracking.py:583-584``; pass it
+    on to ``reductions.percentile(..., value_range=...)``).  ``scale``: optional flat-field scale field
+    ``(Y, X)`` applied in the same pass (see ``flatfield.deskew_flat_field_zyx``); only with ``value_range``.
     """
     torch = _torch()
     if raw_data.dim() != 3:
@@ -177,6 +182,20 @@ def deskew_zyx(raw_data, ls_angle_deg: float, px_to_scan_ratio: float, keep_over
             return out
         fill = _resolve_cval(torch, raw, code, cval, stream)
         Z, Y, X = g.raw_shape
+        if value_range is not None:
+            if (value_range.dtype != torch.float32 or value_range.numel() != 2 or not value_range.is_contiguous()
+                    or value_range.device != raw.device):
+                raise ValueError(f"value_range must be a contiguous float32 tensor of 2 elements on {raw.device}")
+            if scale is not None and (tuple(scale.shape) != (Y, X) or scale.dtype != torch.float32
+                                      or not scale.is_contiguous()):
+                raise ValueError(f"scale must be a contiguous float32 tensor of shape {(Y, X)}")
+            _cabi.check(_cabi.lib().shrimpy_deskew_range_device(
+                raw.data_ptr(), code, scale.data_ptr() if scale is not None else None, out.data_ptr(),
+                value_range.data_ptr(), Z, Y, X, g.out_shape[2], g.n_avg, g.m00, g.m02, g.shift, fill,
+                raw.stride(0), raw.stride(1), _cabi.KERNELS[kernel], stream))
+            return out
+        if scale is not None:
+            raise ValueError("scale is only taken together with value_range; use flatfield.deskew_flat_field_zyx")
         _cabi.check(_cabi.lib().shrimpy_deskew_device(
             raw.data_ptr(), code, out.data_ptr(), Z, Y, X, g.out_shape[2], g.n_avg, g.m00, g.m02, g.shift, fill,
             raw.stride(0), raw.stride(1), 0, 0, _cabi.KERNELS[kernel], stream))

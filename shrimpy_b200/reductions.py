@@ -39,12 +39,21 @@ def value_range(img):
     return lo, hi
 
 
-def percentile(img, percentile: float, nbins: int = 256) -> float:
-    """Histogram estimate of a percentile (0-100): the upper edge of the bin where the CDF reaches it."""
+_range_pass = value_range     # (the keyword of the same name below shadows the function)
+
+
+def percentile(img, percentile: float, nbins: int = 256, value_range=None) -> float:
+    """Histogram estimate of a percentile (0-100): the upper edge of the bin where the CDF reaches it.
+
+    ``value_range``: ``(min, max)`` of ``img`` when already known -- a pair of floats or the two-element tensor
+    ``deskew_zyx(..., value_range=...)`` filled inside the deskew kernel; saves the range pass."""
     if nbins != 256:
         raise NotImplementedError("the histogram kernel has 256 bins, like the reference's default")
     torch, v = _f32_cuda(img)
-    vmin, vmax = value_range(v)
+    if value_range is None:
+        vmin, vmax = _range_pass(v)
+    else:
+        vmin, vmax = (float(x) for x in (value_range.tolist() if hasattr(value_range, "tolist") else value_range))
     if vmax <= vmin:
         return vmin
     with torch.cuda.device(v.device):

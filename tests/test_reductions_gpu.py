@@ -74,3 +74,28 @@ def test_on_a_deskewed_volume_end_to_end():
     want = [(w.sum(axis=tuple(a for a in range(3) if a != ax)) * np.arange(w.shape[ax])).sum() / w.sum() for ax in range(3)]
     got = red.intensity_center_of_mass(vol, background=bg).cpu().numpy()
     assert np.allclose(got, want, rtol=1e-5, atol=1e-4)
+
+
+@pytest.mark.parametrize("n,keep,dtype", [(3, False, "u16"), (1, True, "u16"), (2, True, "f32"), (5, False, "u16")])
+def test_value_range_fused_into_the_deskew(n, keep, dtype):
+    """deskew_zyx(..., value_range=t) fills (min, max) of the result inside the deskew kernel: equal to torch.min /
+    torch.max of the volume (what tracking.py:583-584 computes next), for the TMA and the direct kernel (n = 5),
+    with padding included; the percentile that follows is the same with and without the saved pass."""
+    import torch
+
+    import shrimpy_b200 as sb
+    from shrimpy_b200 import flatfield, reductions
+
+    gen = torch.Generator(device="cuda").manual_seed(n)
+    raw = torch.randint(300, 50000, (150, 23, 192), dtype=torch.int32, device="cuda", generator=gen)
+    raw = raw.to(torch.uint16) if dtype == "u16" else raw.to(torch.float32) * 0.5 - 7000.0
+    rng = torch.empty(2, dtype=torch.float32, device="cuda")
+    out = sb.deskew_zyx(raw, 30.0, 0.39, keep, n, cval=-5.0, value_range=rng)
+    assert torch.equal(out, sb.deskew_zyx(raw, 30.0, 0.39, keep, n, cval=-5.0))
+    assert rng.tolist() == [float(out.min()), float(out.max())]
+    assert reductions.percentile(out, 50.0, value_range=rng) == reductions.percentile(out, 50.0)
+    if dtype == "u16" and n <= 4:
+        scale = flatfield.flat_field_scale(raw)
+        fused = sb.deskew_zyx(raw, 30.0, 0.39, keep, n, cval=-5.0, value_range=rng, scale=scale)
+        assert torch.equal(fused, flatfield.deskew_flat_field_zyx(raw, 30.0, 0.39, keep, n, cval=-5.0, scale=scale))
+        assert rng.tolist() == [float(fused.min()), float(fused.max())]

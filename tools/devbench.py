@@ -214,4 +214,11 @@ if __name__ == "__main__":
         r = {"range_ms": t_ms(lambda: red.value_range(vol)), "percentile_ms": t_ms(lambda: red.percentile(vol, 50.0)),
              "com_ms": t_ms(lambda: red.intensity_center_of_mass(vol, 100.0))}
         r["range_gbs"] = nbytes / r["range_ms"] / 1e6; r["com_gbs"] = nbytes / r["com_ms"] / 1e6
+        gen = torch.Generator(device="cuda").manual_seed(1)
+        raw = torch.randint(100, 60000, (600, 300, 2048), dtype=torch.int32, device="cuda", generator=gen).to(torch.uint16)
+        rng2 = torch.empty(2, dtype=torch.float32, device="cuda")
+        out = torch.empty((100, 2048, 1279), dtype=torch.float32, device="cuda")
+        r["deskew_plain_ms"] = t_ms(lambda: sb.deskew_zyx(raw, 30.0, 0.39, False, 3, out=out), reps=20)
+        r["deskew_with_fused_range_ms"] = t_ms(lambda: sb.deskew_zyx(raw, 30.0, 0.39, False, 3, out=out, value_range=rng2), reps=20)
+        r["percentile_given_range_ms"] = t_ms(lambda: red.percentile(out, 50.0, value_range=rng2))
         print(json.dumps({k: round(v, 3) for k, v in r.items()}), flush=True)
