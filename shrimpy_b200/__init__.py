@@ -9,6 +9,7 @@ deskew helpers it calls).  Public names mirror the ones shrimPy imports; see
 from .deskew import (DeskewGeometry, HostPipeline, deskew_data, deskew_geometry, deskew_window, deskew_zyx,
                      fast_deskew_zyx, get_deskewed_data_shape, window_needs)
 from .settings import DeskewSettings
+from . import flatfield, reductions, register  # noqa: E402,F401  (light: torch is imported lazily inside the calls)
 
 __version__ = "0.1.0"
 
@@ -24,6 +25,9 @@ __all__ = [
     "get_deskewed_data_shape",
     "window_needs",
     "install_biahub_shim",
+    "flatfield",
+    "reductions",
+    "register",
 ]
 
 
