@@ -98,7 +98,21 @@ __global__ void __launch_bounds__(256) com_kernel(const float *__restrict__ v, i
         const int z = (int)(r / Y), y = (int)(r - (long long)z * Y);
         const float *row = v + r * X;
         float w_row = 0.f, wx_row = 0.f;   // float32 within one row (<= 32 * X/32 terms per lane), float64 across rows
-        for (int x = lane; x < X; x += 32) {
+        // eight independent loads in flight per lane (the plain loop was latency-bound at 3.3 TB/s); the sums keep
+        // their sequential order, so the result does not change
+        int x = lane;
+        for (; x + 7 * 32 < X; x += 8 * 32) {
+            float v8[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v8[j] = __ldg(row + x + 32 * j);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float w = fmaxf(v8[j] - background, 0.f);
+                w_row += w;
+                wx_row = fmaf(w, (float)(x + 32 * j), wx_row);
+            }
+        }
+        for (; x < X; x += 32) {
             const float w = fmaxf(__ldg(row + x) - background, 0.f);
             w_row += w;
             wx_row = fmaf(w, (float)x, wx_row);
