@@ -137,29 +137,69 @@ struct Chunk<uint16_t> {
     static __device__ __forceinline__ void fast(const uint8_t *tile, const uint32_t *off0, const uint32_t *off1,
                                                 const uint32_t *sw0, const uint32_t *sw1, const float *w,
                                                 const float *u, uint32_t cbyte, float inv_n, float *out) {
-        uint32_t sum[kElems];
-        float W[kElems];
+        if constexpr (NAVG >= 4) {
+            // four rows per voxel: the scalar sequence keeps fewer values live (measured 3-6 % faster than the packed one)
+            uint32_t sum[kElems];
+            float W[kElems];
 #pragma unroll
-        for (int k = 0; k < NAVG; ++k) {
-            const uint4 A = *reinterpret_cast<const uint4 *>(tile + off0[k] + (cbyte ^ sw0[k]));
-            const uint4 B = *reinterpret_cast<const uint4 *>(tile + off1[k] + (cbyte ^ sw1[k]));
+            for (int k = 0; k < NAVG; ++k) {
+                const uint4 A = *reinterpret_cast<const uint4 *>(tile + off0[k] + (cbyte ^ sw0[k]));
+                const uint4 B = *reinterpret_cast<const uint4 *>(tile + off1[k] + (cbyte ^ sw1[k]));
 #pragma unroll
-            for (int j = 0; j < kElems; ++j) {
-                const uint32_t am = magic(A, j), bm = magic(B, j);
-                const float d = __uint_as_float(bm) - __uint_as_float(am);  // exact: both are 2^23 + integer
-                if (NAVG == 1) {
-                    out[j] = fmaf(w[0], d, __uint_as_float(am) - 8388608.0f);
-                } else {
-                    sum[j] = (k == 0) ? am : sum[j] + am;
-                    W[j] = (k == 0) ? u[0] * d : fmaf(u[k], d, W[j]);
+                for (int j = 0; j < kElems; ++j) {
+                    const uint32_t am = magic(A, j), bm = magic(B, j);
+                    const float d = __uint_as_float(bm) - __uint_as_float(am);  // exact: both are 2^23 + integer
+                    if (NAVG == 1) {
+                        out[j] = fmaf(w[0], d, __uint_as_float(am) - 8388608.0f);
+                    } else {
+                        sum[j] = (k == 0) ? am : sum[j] + am;
+                        W[j] = (k == 0) ? u[0] * d : fmaf(u[k], d, W[j]);
+                    }
                 }
             }
-        }
-        if (NAVG > 1) {
+            if (NAVG > 1) {
 #pragma unroll
-            for (int j = 0; j < kElems; ++j) {
-                const float S = __uint_as_float(sum[j] - (uint32_t)(NAVG - 1) * kMagic) - 8388608.0f;
-                out[j] = fmaf(S, inv_n, W[j]);
+                for (int j = 0; j < kElems; ++j) {
+                    const float S = __uint_as_float(sum[j] - (uint32_t)(NAVG - 1) * kMagic) - 8388608.0f;
+                    out[j] = fmaf(S, inv_n, W[j]);
+                }
+            }
+        } else {
+            // Pairs of x positions go through packed float32 arithmetic (FADD2 / FFMA2 on sm_100: half the issue slots,
+            // the same rounding per half as the scalar sequence, so the results are bit-identical to every other path).
+            uint32_t sum[kElems];
+            float2 W2[kElems / 2];
+#pragma unroll
+            for (int k = 0; k < NAVG; ++k) {
+                const uint4 A = *reinterpret_cast<const uint4 *>(tile + off0[k] + (cbyte ^ sw0[k]));
+                const uint4 B = *reinterpret_cast<const uint4 *>(tile + off1[k] + (cbyte ^ sw1[k]));
+#pragma unroll
+                for (int j = 0; j < kElems; j += 2) {
+                    const uint32_t am0 = magic(A, j), am1 = magic(A, j + 1), bm0 = magic(B, j), bm1 = magic(B, j + 1);
+                    const float2 a2 = make_float2(__uint_as_float(am0), __uint_as_float(am1));
+                    const float2 b2 = make_float2(__uint_as_float(bm0), __uint_as_float(bm1));
+                    const float2 d2 = __fadd2_rn(b2, make_float2(-a2.x, -a2.y));   // exact: both are 2^23 + integer
+                    if (NAVG == 1) {
+                        const float2 r = __ffma2_rn(make_float2(w[0], w[0]), d2, __fadd2_rn(a2, make_float2(-8388608.0f, -8388608.0f)));
+                        out[j] = r.x;
+                        out[j + 1] = r.y;
+                    } else {
+                        sum[j] = (k == 0) ? am0 : sum[j] + am0;
+                        sum[j + 1] = (k == 0) ? am1 : sum[j + 1] + am1;
+                        W2[j / 2] = (k == 0) ? __fmul2_rn(make_float2(u[0], u[0]), d2) : __ffma2_rn(make_float2(u[k], u[k]), d2, W2[j / 2]);
+                    }
+                }
+            }
+            if (NAVG > 1) {
+#pragma unroll
+                for (int j = 0; j < kElems; j += 2) {
+                    const float2 m2 = make_float2(__uint_as_float(sum[j] - (uint32_t)(NAVG - 1) * kMagic),
+                                                  __uint_as_float(sum[j + 1] - (uint32_t)(NAVG - 1) * kMagic));
+                    const float2 S2 = __fadd2_rn(m2, make_float2(-8388608.0f, -8388608.0f));
+                    const float2 r = __ffma2_rn(S2, make_float2(inv_n, inv_n), W2[j / 2]);
+                    out[j] = r.x;
+                    out[j + 1] = r.y;
+                }
             }
         }
     }
