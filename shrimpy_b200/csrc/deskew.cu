@@ -221,21 +221,27 @@ struct Chunk<float> {
     static __device__ __forceinline__ void fast(const uint8_t *tile, const uint32_t *off0, const uint32_t *off1,
                                                 const uint32_t *sw0, const uint32_t *sw1, const float *w,
                                                 const float *u, uint32_t cbyte, float inv_n, float *out) {
-        float S[kElems], W[kElems], one[kElems];
+        // packed pairs (FADD2 / FFMA2): the same operations and rounding as the scalar sequence of the other kernels
+        float2 S2[kElems / 2], W2[kElems / 2], one2[kElems / 2];
 #pragma unroll
         for (int k = 0; k < NAVG; ++k) {
             const uint4 A = *reinterpret_cast<const uint4 *>(tile + off0[k] + (cbyte ^ sw0[k]));
             const uint4 B = *reinterpret_cast<const uint4 *>(tile + off1[k] + (cbyte ^ sw1[k]));
 #pragma unroll
-            for (int j = 0; j < kElems; ++j) {
-                const float a = get(A, j), d = get(B, j) - a;
-                S[j] = (k == 0) ? a : S[j] + a;
-                W[j] = (k == 0) ? u[0] * d : fmaf(u[k], d, W[j]);
-                if (k == 0) one[j] = fmaf(w[0], d, a);
+            for (int j = 0; j < kElems; j += 2) {
+                const float2 a2 = make_float2(get(A, j), get(A, j + 1)), b2 = make_float2(get(B, j), get(B, j + 1));
+                const float2 d2 = __fadd2_rn(b2, make_float2(-a2.x, -a2.y));
+                S2[j / 2] = (k == 0) ? a2 : __fadd2_rn(S2[j / 2], a2);
+                W2[j / 2] = (k == 0) ? __fmul2_rn(make_float2(u[0], u[0]), d2) : __ffma2_rn(make_float2(u[k], u[k]), d2, W2[j / 2]);
+                if (k == 0 && NAVG == 1) one2[j / 2] = __ffma2_rn(make_float2(w[0], w[0]), d2, a2);
             }
         }
 #pragma unroll
-        for (int j = 0; j < kElems; ++j) out[j] = (NAVG == 1) ? one[j] : fmaf(S[j], inv_n, W[j]);
+        for (int j = 0; j < kElems; j += 2) {
+            const float2 r = (NAVG == 1) ? one2[j / 2] : __ffma2_rn(S2[j / 2], make_float2(inv_n, inv_n), W2[j / 2]);
+            out[j] = r.x;
+            out[j + 1] = r.y;
+        }
     }
 };
 
