@@ -8,8 +8,9 @@ work shards naturally, one halo exchange where it does not (SURVEY.md section 8e
   along the scan axis: rank g owns a contiguous range of raw scan slices and computes a contiguous
   range of output columns (o2).  Because of the shear, its columns also read up to
   ``r cos(theta) (Y-1) + 1`` slices below its own range (owned by the previous rank(s)) and at most
-  two above; those halos travel peer-to-peer (``torch.distributed`` send/recv: NCCL over
-  NVLink/NVSwitch on GPUs, gloo in the CPU tests).  Output columns whose taps lie entirely in the
+  two above; those halos travel peer-to-peer: PULLED from the neighbour's HBM by a device copy over
+  peer-mapped (symmetric) memory when the slab is a ``PeerSlab`` (NVLink / NVSwitch loads, no NCCL
+  call on the data path), else ``torch.distributed`` send/recv (NCCL on GPUs, gloo in the CPU tests).  Output columns whose taps lie entirely in the
   rank's own slices are computed while the halo is in flight.
 
 The arithmetic is always the full-stack geometry (window calls), so the concatenated result is
@@ -25,7 +26,8 @@ import numpy as np
 
 from .deskew import DeskewGeometry, window_needs
 
-__all__ = ["shard_units", "ScanShard", "plan_scan_split", "exchange_halos", "deskew_scan_split"]
+__all__ = ["shard_units", "ScanShard", "plan_scan_split", "exchange_halos", "deskew_scan_split", "PeerSlab",
+           "exchange_halos_peer"]
 
 
 def shard_units(units: Sequence, world_size: int, rank: int) -> list:
@@ -155,8 +157,70 @@ def exchange_halos(own_slab, shards: Sequence[ScanShard], rank: int, *, group=No
     return slabs[0], slabs[1], reqs
 
 
+class PeerSlab:
+    """This rank's raw slices in peer-mapped (symmetric) device memory: every rank of the box can read them with
+    plain loads over NVLink / NVSwitch, so the halo of a scan-axis split is PULLED by a device copy -- no NCCL call,
+    no staging, nothing for the owner to do.  One allocation of the same size on every rank (the largest slab),
+    one rendezvous; ``tensor`` is the view holding this rank's ``own_z`` slices."""
+
+    def __init__(self, shards: Sequence[ScanShard], rank: int, frame_shape: Tuple[int, int], dtype, device, group=None):
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+
+        self.shards, self.rank, self.frame_shape, self.dtype = list(shards), rank, tuple(frame_shape), dtype
+        self.itemsize = torch.empty((), dtype=dtype).element_size()
+        frame_bytes = frame_shape[0] * frame_shape[1] * self.itemsize
+        nbytes = max(1, max(s.own_z[1] - s.own_z[0] for s in shards)) * frame_bytes
+        self._buf = symm_mem.empty(nbytes, dtype=torch.uint8, device=device)
+        self._hdl = symm_mem.rendezvous(self._buf, group if group is not None else dist.group.WORLD)
+        self.tensor = self._view(self._buf, shards[rank])
+
+    def _view(self, flat, shard: ScanShard):
+        nz = shard.own_z[1] - shard.own_z[0]
+        nbytes = nz * self.frame_shape[0] * self.frame_shape[1] * self.itemsize
+        return flat[:nbytes].view(self.dtype).view((nz,) + self.frame_shape)
+
+    def peer(self, other_rank: int):
+        """Rank ``other_rank``'s slices as a tensor on THIS device (loads go over NVLink)."""
+        import torch
+
+        flat = self._hdl.get_buffer(other_rank, (self._buf.numel(),), torch.uint8)
+        return self._view(flat, self.shards[other_rank])
+
+    def barrier(self) -> None:
+        """Device-side barrier over the ranks on the current stream (call after filling ``tensor``, before peers read)."""
+        self._hdl.barrier()
+
+
+def exchange_halos_peer(slab: "PeerSlab", shards: Sequence[ScanShard], rank: int, stream=None):
+    """The peer-memory form of ``exchange_halos``: the slabs for the boundary column ranges are assembled by device
+    copies that read the neighbours' slices directly from their HBM (on ``stream`` when given, so that the interior
+    columns are computed meanwhile).  Returns ``((low_slab, low_z0), (high_slab, high_z0), event)``."""
+    import torch
+
+    me = shards[rank]
+    own = slab.tensor
+    ctx = torch.cuda.stream(stream) if stream is not None else torch.cuda.stream(torch.cuda.current_stream())
+    if stream is not None:
+        stream.wait_stream(torch.cuda.current_stream())
+    out = []
+    with ctx:
+        for z0, z1 in (me.low_need_z, me.high_need_z):
+            piece = torch.empty((max(z1 - z0, 0),) + tuple(own.shape[1:]), dtype=own.dtype, device=own.device)
+            for other in shards:
+                a, b = max(z0, other.own_z[0]), min(z1, other.own_z[1])
+                if b > a:
+                    src = own if other.rank == rank else slab.peer(other.rank)
+                    piece[a - z0:b - z0].copy_(src[a - other.own_z[0]:b - other.own_z[0]], non_blocking=True)
+            out.append((piece, z0))
+        event = torch.cuda.Event()
+        event.record()
+    return out[0], out[1], event
+
+
 def deskew_scan_split(own_slab, g: DeskewGeometry, shards: Sequence[ScanShard], rank: int, *, cval: float = 0.0,
-                      group=None, window_fn: Optional[Callable] = None):
+                      group=None, window_fn: Optional[Callable] = None, peer_stream=None):
     """Deskew this rank's output columns of one volume that is split along the scan axis.
 
     Returns the compact tensor ``out[:, :, c0:c1]``.  ``window_fn(slab, g, p_begin, p_count, c_begin,
@@ -177,7 +241,8 @@ def deskew_scan_split(own_slab, g: DeskewGeometry, shards: Sequence[ScanShard], 
     me = shards[rank]
     Yn, X, _ = g.out_shape
     c0, c1 = me.cols
-    out = torch.empty((Yn, X, c1 - c0), dtype=torch.float32, device=own_slab.device)
+    device = own_slab.tensor.device if isinstance(own_slab, PeerSlab) else own_slab.device
+    out = torch.empty((Yn, X, c1 - c0), dtype=torch.float32, device=device)
 
     def run(slab, z_origin, a, b):
         if b <= a:
@@ -190,6 +255,15 @@ def deskew_scan_split(own_slab, g: DeskewGeometry, shards: Sequence[ScanShard], 
         else:
             view.copy_(window_fn(slab, g, 0, Yn, a, b - a, 0, z_origin, cval))
 
+    if isinstance(own_slab, PeerSlab):
+        # halo pulled from the neighbours' HBM by device copies on a side stream (no NCCL on the data path)
+        peer, own_slab = own_slab, own_slab.tensor
+        (low, low_z0), (high, high_z0), ready = exchange_halos_peer(peer, shards, rank, stream=peer_stream)
+        run(own_slab, me.own_z[0], *me.interior_cols)     # overlaps with the pull
+        torch.cuda.current_stream().wait_event(ready)
+        run(low, low_z0, *me.low_cols)
+        run(high, high_z0, *me.high_cols)
+        return out
     (low, low_z0), (high, high_z0), reqs = exchange_halos(own_slab, shards, rank, group=group)
     run(own_slab, me.own_z[0], *me.interior_cols)     # overlaps with the exchange
     for r in reqs:
