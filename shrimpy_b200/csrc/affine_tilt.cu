@@ -11,8 +11,10 @@
 //   * every CTA tabulates, per step (one thread per step, float64 corner arithmetic): the planes that must have
 //     landed / may be handed back, the coordinate of the tile's first voxel relative to (ring origin, box origin)
 //     in 9.23 fixed point, and a CLASS: "fast" (every voxel of the tile strictly inside the input: no per-voxel
-//     test at all), "outside" (constant fill) or "mixed" (the tile straddles the rim: every voxel goes through
-//     tilt_exact_voxel, scipy's exact arithmetic and edge rule from the output index).
+//     test at all), "outside" (constant fill) or "mixed" (the tile straddles the rim: voxels are classified one by
+//     one with a float32 coordinate and a 0.05 margin -- safely interior ones take the fast arithmetic, safely
+//     outside ones the pad value, the thin shell in between goes through tilt_exact_voxel, scipy's exact float64
+//     arithmetic and edge rule from the output index).
 // A voxel of a fast step is  base(step) + offset(column)  in 32-bit fixed point: one integer add per axis; floor,
 // ring slot, in-box offset and the 23-bit lerp weight are bit fields of the sum.  Nothing accumulates: the error
 // against scipy's float64 coordinate is < 2e-7 voxel (the weight itself has 23 bits), harmless strictly inside the
@@ -80,6 +82,9 @@ struct StepInfo {
     unsigned bz, by, bx;   // coordinate of the tile's first voxel relative to (ring origin, box origin), 9.23 fixed point
     unsigned ctl;          // bits 0-11: planes [0, need) must have landed; 12-23: planes [0, rel) may be handed back; 24-25: class
 };
+struct StepCoarse {
+    float z, y, x, pad;    // the same voxel's absolute coordinate in float32 (mixed steps classify voxels with it)
+};
 enum { kStepMixed = 0, kStepFast = 1, kStepOutside = 2 };
 
 __device__ __forceinline__ void tilt_consumer_sync() {
@@ -109,6 +114,7 @@ __global__ void __launch_bounds__(kTiltThreads, (IA * RB <= 4) ? 3 : 2)
     extern __shared__ __align__(128) float smem_raw[];
     __shared__ __align__(8) uint64_t full[kTiltMaxRing], empty[kTiltMaxRing];
     __shared__ __align__(16) StepInfo tab[kTiltMaxSteps];
+    __shared__ __align__(16) StepCoarse coarse[kTiltMaxSteps];
     __shared__ int s_zmin, s_zmax;
     float *ring = smem_raw + (((128u - (smem_u32(smem_raw) & 127u)) & 127u) >> 2);
     const uint32_t full_s = smem_u32(full), empty_s = smem_u32(empty), ring_s = smem_u32(ring);
@@ -199,6 +205,9 @@ __global__ void __launch_bounds__(kTiltThreads, (IA * RB <= 4) ? 3 : 2)
         e.bx = (unsigned)__double2ll_rd((c0[2] - (double)ox0) * 8388608.0);
         e.ctl = need | (rel << 12) | ((unsigned)cls << 24);
         tab[tid] = e;
+        StepCoarse f;
+        f.z = (float)c0[0]; f.y = (float)c0[1]; f.x = (float)c0[2]; f.pad = 0.f;
+        coarse[tid] = f;
     }
     __syncthreads();
 
@@ -310,13 +319,40 @@ __global__ void __launch_bounds__(kTiltThreads, (IA * RB <= 4) ? 3 : 2)
 #pragma unroll
             for (int c = 0; c < NC; ++c) res[c] = cval;
         } else {
-            // the tile straddles the rim of the input (or of the output grid) at this step: every voxel exactly
+            // The tile straddles the rim of the input (or of the output grid) at this step.  Each voxel is classified
+            // with its coordinate in float32 (good to ~2e-3 for coordinates below 2^13, margin 0.05): safely interior ->
+            // the same 9.23 arithmetic as a fast step (scalar); safely outside -> cval; within the margin of the rim ->
+            // tilt_exact_voxel (scipy's exact float64 arithmetic and edge rule from the output index).
+            const StepCoarse f = coarse[lz];
+            const float dz = (float)P.iz - 1.0f, dy = (float)P.iy - 1.0f, dx = (float)P.ix - 1.0f;
 #pragma unroll
             for (int c = 0; c < NC; ++c) {
-                res[c] = cval;
-                if (live >> c & 1u)
-                    res[c] = tilt_exact_voxel(ring, &P, t0z + lz, t0y + (SWAP ? lane + 32 * (c % IA) : warp + 8 * (c / IA)),
-                                                      t0x + (SWAP ? warp + 8 * (c / IA) : lane + 32 * (c % IA)), oy0, ox0, CLEAN);
+                float r = cval;
+                if (live >> c & 1u) {
+                    const float fz = f.z + (float)(int)lz32[c] * 1.1920928955078125e-7f;
+                    const float fy = f.y + (float)(int)ly32[c] * 1.1920928955078125e-7f;
+                    const float fx = f.x + (float)(int)lx32[c] * 1.1920928955078125e-7f;
+                    const float m = 0.05f + 2e-6f * fmaxf(dz, fmaxf(dy, dx));   // float32 coordinate error grows with the size
+                    const bool inner = fz >= m && fz <= dz - m && fy >= m && fy <= dy - m && fx >= m && fx <= dx - m;
+                    const bool outer = fz < -m || fz > dz + m || fy < -m || fy > dy + m || fx < -m || fx > dx + m;
+                    if (inner) {
+                        const unsigned cz = e.bz + lz32[c], cy = e.by + ly32[c], cx = e.bx + lx32[c];
+                        const float wz = frac23(cz, one_bits), wy = frac23(cy, one_bits), wx = frac23(cx, one_bits);
+                        const unsigned inpl = (cy >> 23) * pitch4 + (ring_s + ((cx >> 23) << 2));
+                        const unsigned sa = (cz >> 23) & mask, sb = (sa + 1u) & mask;
+                        const unsigned oa = sa * slot_bytes + inpl, ob = sb * slot_bytes + inpl;
+                        const float a00 = lds_f32<0>(oa), a01 = lds_f32<4>(oa), a10 = lds_f32<0>(oa + pitch4), a11 = lds_f32<4>(oa + pitch4);
+                        const float b00 = lds_f32<0>(ob), b01 = lds_f32<4>(ob), b10 = lds_f32<0>(ob + pitch4), b11 = lds_f32<4>(ob + pitch4);
+                        const float xa0 = fmaf(wx, a01 - a00, a00), xa1 = fmaf(wx, a11 - a10, a10);
+                        const float xb0 = fmaf(wx, b01 - b00, b00), xb1 = fmaf(wx, b11 - b10, b10);
+                        const float va = fmaf(wy, xa1 - xa0, xa0), vb = fmaf(wy, xb1 - xb0, xb0);
+                        r = fmaf(wz, vb - va, va);
+                    }
+                    if ((!inner && !outer) || (CLEAN && inner && nonfinite(r)))
+                        r = tilt_exact_voxel(ring, &P, t0z + lz, t0y + (SWAP ? lane + 32 * (c % IA) : warp + 8 * (c / IA)),
+                                             t0x + (SWAP ? warp + 8 * (c / IA) : lane + 32 * (c % IA)), oy0, ox0, CLEAN);
+                }
+                res[c] = r;
             }
         }
         if (SWAP) {
