@@ -217,6 +217,14 @@ __global__ void __launch_bounds__(kStreamThreads, (IA * RB <= 4) ? 3 : 2)
     const long long plane = (long long)P.oy * P.ox;
     float *pstep = P.out + (long long)t0z * plane;        // start of output plane t0z (advanced per step)
     float *pcol = pstep + (long long)(t0y + warp) * P.ox + t0x + lane;   // !SWAP: this thread's column c = 0
+    // SWAP: the drain of a step's transposed tile.  A thread always drains the same o2 column b and rows a, a + R,
+    // a + 2R, ... (R = consumers / LB), so its shared offset and global pointer are set up once and only stepped.
+    constexpr int kDrainRows = kStreamConsumers / LB, kDrainIters = LA / kDrainRows;
+    const int drain_a = tid / LB, drain_b = tid % LB;
+    const bool drain_full = t0y + TY <= P.oy && t0x + TX <= P.ox;
+    const bool drain_col_ok = t0x + drain_b < P.ox;
+    float *pdrain = pstep + (long long)(t0y + drain_a) * P.ox + t0x + drain_b;
+    const long long drain_stride = (long long)kDrainRows * P.ox;
 
     float2 V0[NC2], V1[NC2];       // plane values: V0 <- planes with even sequence number, V1 <- odd
 #pragma unroll
@@ -226,7 +234,7 @@ __global__ void __launch_bounds__(kStreamThreads, (IA * RB <= 4) ? 3 : 2)
     const float cval = P.cval;
     int outside_steps = 0;
 
-    for (int lz = 0; lz < nsteps; ++lz, pstep += plane, pcol += plane) {
+    for (int lz = 0; lz < nsteps; ++lz, pstep += plane, pcol += plane, pdrain += plane) {
         const ZStep e = T.e[lz];
         if (!e.inside) {   // written by the constant-fill pass below
             ++outside_steps;
@@ -319,11 +327,14 @@ __global__ void __launch_bounds__(kStreamThreads, (IA * RB <= 4) ? 3 : 2)
 #pragma unroll
             for (int c = 0; c < NC; ++c) ot[(lane + 32 * (c % IA)) * (LB + 1) + warp + 8 * (c / IA)] = res[c];
             consumer_sync();   // one barrier per step: the other buffer is written while this one drains
+            {
+                const float *src = ot + drain_a * (LB + 1) + drain_b;
+                float *dst = pdrain;
 #pragma unroll
-            for (int idx = tid; idx < LA * LB; idx += kStreamConsumers) {
-                const int a = idx / LB, b = idx % LB;
-                const int o1 = t0y + a, o2 = t0x + b;
-                if (o1 < P.oy && o2 < P.ox) __stcs(pstep + (long long)o1 * P.ox + o2, ot[a * (LB + 1) + b]);
+                for (int i = 0; i < kDrainIters; ++i) {
+                    if (drain_full || (drain_col_ok && t0y + drain_a + i * kDrainRows < P.oy)) __stcs(dst, src[i * kDrainRows * (LB + 1)]);
+                    dst += drain_stride;
+                }
             }
         }
     }

@@ -263,12 +263,20 @@ __global__ void __launch_bounds__(tilt_threads(SWAP), (IA * RB <= 4) ? 3 : 2)
     const long long plane = (long long)P.oy * P.ox;
     float *pstep = P.out + (long long)t0z * plane;                         // output plane of the current step
     float *pcol = pstep + (long long)(t0y + warp) * P.ox + t0x + lane;      // !SWAP: this thread's column c = 0
+    // SWAP: the drain of a step's transposed tile.  A thread always drains the same o2 column b and rows a, a + R,
+    // a + 2R, ... (R = consumers / LB), so its shared offset and global pointer are set up once and only stepped.
+    constexpr int kDrainRows = kTiltConsumers / LB, kDrainIters = LA / kDrainRows;
+    const int drain_a = tid / LB, drain_b = tid % LB;
+    const bool drain_full = t0y + TY <= P.oy && t0x + TX <= P.ox;
+    const bool drain_col_ok = t0x + drain_b < P.ox;
+    float *pdrain = pstep + (long long)(t0y + drain_a) * P.ox + t0x + drain_b;
+    const long long drain_stride = (long long)kDrainRows * P.ox;
     const float cval = P.cval;
     unsigned ready = 0, released = 0;             // planes [0, ready) have landed; planes [0, released) were handed back
     unsigned rslot = (unsigned)zstart & mask;      // slot of plane `ready`
     unsigned eslot = rslot;                        // slot of plane `released`
 
-    for (int lz = 0; lz < nsteps; ++lz, pcol += plane, pstep += plane) {
+    for (int lz = 0; lz < nsteps; ++lz, pcol += plane, pstep += plane, pdrain += plane) {
         const StepInfo e = tab[lz];
         const unsigned need = e.ctl & 0xfffu, rel = (e.ctl >> 12) & 0xfffu, cls = e.ctl >> 24;
 #pragma unroll 1
@@ -388,11 +396,14 @@ __global__ void __launch_bounds__(tilt_threads(SWAP), (IA * RB <= 4) ? 3 : 2)
 #pragma unroll
             for (int c = 0; c < NC; ++c) ot[(lane + 32 * (c % IA)) * (LB + 1) + warp + 8 * (c / IA)] = res[c];
             tilt_consumer_sync();   // one barrier per step: the other buffer is written while this one drains
+            {
+                const float *src = ot + drain_a * (LB + 1) + drain_b;
+                float *dst = pdrain;
 #pragma unroll
-            for (int idx = tid; idx < LA * LB; idx += kTiltConsumers) {
-                const int a = idx / LB, b = idx % LB;
-                const int o1 = t0y + a, o2 = t0x + b;
-                if (o1 < P.oy && o2 < P.ox) __stcs(pstep + (long long)o1 * P.ox + o2, ot[a * (LB + 1) + b]);
+                for (int i = 0; i < kDrainIters; ++i) {
+                    if (drain_full || (drain_col_ok && t0y + drain_a + i * kDrainRows < P.oy)) __stcs(dst, src[i * kDrainRows * (LB + 1)]);
+                    dst += drain_stride;
+                }
             }
         } else if (tile_full) {
 #pragma unroll
