@@ -162,6 +162,17 @@ int shrimpy_deskew_range_device(const void *d_raw, int raw_dtype, const float *d
  */
 int shrimpy_affine_device(const float *d_in, float *d_out, int iz, int iy, int ix, int oz, int oy, int ox,
                           const double M[12], float cval, int nan_to_zero, void *stream);
+/*
+ * The same resample from an input whose rows / planes are padded: element (z,y,x) at
+ * d_in[z*in_stride_z + y*in_stride_y + x] (strides in elements, multiples of 4 so that rows start on 16-byte
+ * boundaries).  The plane-streaming kernels read through a tensor map, which takes the strides and zero-fills
+ * beyond the logical ix; this is how inputs whose X is not a multiple of 4 (e.g. a deskewed (100,2048,1279) volume)
+ * reach them -- the Python layer pads the rows once.  Returns SHRIMPY_EINVAL ("not eligible") when the matrix needs
+ * one of the dense-only kernels; the caller then uses shrimpy_affine_device on the dense array.
+ */
+int shrimpy_affine_strided_device(const float *d_in, float *d_out, int iz, int iy, int ix, int64_t in_stride_z,
+                                  int64_t in_stride_y, int oz, int oy, int ox, const double M[12], float cval,
+                                  int nan_to_zero, void *stream);
 
 /*
  * Reductions over a deskewed float32 volume used by the tracking step that consumes it

@@ -33,6 +33,7 @@ EXPORTS = (
     "shrimpy_deskew_flatfield_device",
     "shrimpy_deskew_range_device",
     "shrimpy_affine_device",
+    "shrimpy_affine_strided_device",
     "shrimpy_minmax_device",
     "shrimpy_hist256_device",
     "shrimpy_center_of_mass_device",
@@ -103,6 +104,9 @@ def _declare(lib) -> None:
     lib.shrimpy_affine_device.restype = c_int
     lib.shrimpy_affine_device.argtypes = [c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int,
                                           ctypes.POINTER(c_dbl), c_flt, c_int, c_vp]
+    lib.shrimpy_affine_strided_device.restype = c_int
+    lib.shrimpy_affine_strided_device.argtypes = [c_vp, c_vp, c_int, c_int, c_int, c_i64, c_i64, c_int, c_int, c_int,
+                                                  ctypes.POINTER(c_dbl), c_flt, c_int, c_vp]
     lib.shrimpy_minmax_device.restype = c_int
     lib.shrimpy_minmax_device.argtypes = [c_vp, c_i64, c_vp, c_vp]
     lib.shrimpy_hist256_device.restype = c_int

@@ -345,8 +345,8 @@ static bool choose_tile(AffineParams &P, int smem_limit, bool tma) {
 
 using namespace shrimpy;
 
-extern "C" int shrimpy_affine_device(const float *d_in, float *d_out, int iz, int iy, int ix, int oz, int oy,
-                                     int ox, const double M[12], float cval, int nan_to_zero, void *stream) {
+static int affine_impl(const float *d_in, float *d_out, int iz, int iy, int ix, long long in_sz, long long in_sy, int oz,
+                       int oy, int ox, const double M[12], float cval, int nan_to_zero, void *stream) {
     if (iz <= 0 || iy <= 0 || ix <= 0 || oz < 0 || oy < 0 || ox < 0)
         return fail(SHRIMPY_EINVAL, "affine: bad shape in=(%d,%d,%d) out=(%d,%d,%d)", iz, iy, ix, oz, oy, ox);
     if (!M) return fail(SHRIMPY_EINVAL, "affine: null matrix");
@@ -361,6 +361,9 @@ extern "C" int shrimpy_affine_device(const float *d_in, float *d_out, int iz, in
     for (int i = 0; i < 12; ++i) P.M[i] = M[i];
     P.cval = cval;
     P.nan_to_zero = nan_to_zero;
+    const bool dense = in_sy == ix && in_sz == (long long)ix * iy;
+    P.in_sy = in_sy;
+    P.in_sz = in_sz;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
 
     const char *force = getenv("SHRIMPY_AFFINE_KERNEL");
@@ -385,6 +388,8 @@ extern "C" int shrimpy_affine_device(const float *d_in, float *d_out, int iz, in
         if (rc != SHRIMPY_OK || launched) return rc;
         if (force && force[1] == '!') return fail(SHRIMPY_EINVAL, "affine: the tilt kernel was forced but is not eligible");
     }
+    if (!dense)   // only the plane-streaming kernels take row / plane strides (through the tensor map)
+        return fail(SHRIMPY_EINVAL, "affine: strided input is not eligible for the streaming kernels");
     const int smem_limit = 56 * 1024;  // 4 CTAs per SM: staging of one tile overlaps the maths of others
     // TMA staging (dense pitch) when a warp's 32 consecutive o2 touch only a few input rows and the
     // tensor map constraints hold; otherwise cp.async rows at an odd pitch.
@@ -444,4 +449,17 @@ extern "C" int shrimpy_affine_device(const float *d_in, float *d_out, int iz, in
     count_launch();
     SHRIMPY_CUDA_TRY(cudaGetLastError());
     return SHRIMPY_OK;
+}
+
+extern "C" int shrimpy_affine_device(const float *d_in, float *d_out, int iz, int iy, int ix, int oz, int oy,
+                                     int ox, const double M[12], float cval, int nan_to_zero, void *stream) {
+    return affine_impl(d_in, d_out, iz, iy, ix, (long long)ix * iy, ix, oz, oy, ox, M, cval, nan_to_zero, stream);
+}
+
+extern "C" int shrimpy_affine_strided_device(const float *d_in, float *d_out, int iz, int iy, int ix,
+                                             int64_t in_stride_z, int64_t in_stride_y, int oz, int oy, int ox,
+                                             const double M[12], float cval, int nan_to_zero, void *stream) {
+    if (in_stride_y < ix || in_stride_z < in_stride_y * iy)
+        return fail(SHRIMPY_EINVAL, "affine: input strides smaller than the row / plane");
+    return affine_impl(d_in, d_out, iz, iy, ix, in_stride_z, in_stride_y, oz, oy, ox, M, cval, nan_to_zero, stream);
 }

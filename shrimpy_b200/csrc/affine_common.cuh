@@ -21,6 +21,7 @@ struct AffineParams {
     unsigned tma_bytes;     // bytes one TMA box load delivers
     int LA, LB;             // planar kernel: tile extent along the lane axis / the other in-plane axis
     int ring_log2, PB, ZC;  // stream kernel: log2(planes in the ring), floats per ring slot, output steps per CTA
+    long long in_sy, in_sz; // element strides of the input rows / planes (stream and tilt kernels; ix, ix*iy when dense)
 };
 
 constexpr int kAffThreads = 128;

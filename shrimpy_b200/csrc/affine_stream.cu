@@ -400,7 +400,7 @@ int launch_affine_stream(AffineParams P, int nan_to_zero, cudaStream_t s, bool *
     *launched = false;
     const double *M = P.M;
     if (!(M[1] == 0.0 && M[2] == 0.0 && M[4] == 0.0 && M[8] == 0.0)) return SHRIMPY_OK;
-    if ((reinterpret_cast<uintptr_t>(P.in) & 15u) != 0 || P.ix % 4 != 0 || (long long)P.oy * P.ox >= 2147483647LL ||
+    if ((reinterpret_cast<uintptr_t>(P.in) & 15u) != 0 || P.in_sy % 4 != 0 || P.in_sz % 4 != 0 || (long long)P.oy * P.ox >= 2147483647LL ||
         tensor_map_encoder() == nullptr)
         return SHRIMPY_OK;
     const bool swap = std::fabs(M[9]) > std::fabs(M[10]);   // input x follows o1 more than o2: lanes along o1
@@ -451,7 +451,7 @@ int launch_affine_stream(AffineParams P, int nan_to_zero, cudaStream_t s, bool *
 
     CUtensorMap tmap{};
     const cuuint64_t gdim[3] = {(cuuint64_t)P.ix, (cuuint64_t)P.iy, (cuuint64_t)P.iz};
-    const cuuint64_t gstride[2] = {(cuuint64_t)P.ix * 4, (cuuint64_t)P.ix * P.iy * 4};
+    const cuuint64_t gstride[2] = {(cuuint64_t)P.in_sy * 4, (cuuint64_t)P.in_sz * 4};   // rows beyond ix are zero-filled by TMA
     const cuuint32_t bdim[3] = {(cuuint32_t)P.BX, (cuuint32_t)P.BY, 1u};
     const cuuint32_t estr[3] = {1u, 1u, 1u};
     P.tma_bytes = bdim[0] * bdim[1] * 4u;

@@ -19,6 +19,9 @@ from . import _cabi
 
 __all__ = ["apply_affine_transform", "affine_transform_zyx"]
 
+# below this size the dense-only kernels are as fast as padding the rows for the streaming ones
+_PAD_MIN_VOXELS = 1 << 22
+
 
 def _matrix12(matrix) -> np.ndarray:
     M = np.asarray(matrix, dtype=np.float64)
@@ -57,10 +60,24 @@ def affine_transform_zyx(zyx_data, matrix, output_shape_zyx: Sequence[int], cval
             return out
         if vol.numel() == 0:
             raise ValueError("empty input volume")
+        Mp = M.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+        stream = torch.cuda.current_stream().cuda_stream
+        iz, iy, ix = vol.shape
+        if ix % 4 != 0 and vol.numel() >= _PAD_MIN_VOXELS:
+            # The plane-streaming kernels stage planes with TMA, which wants rows on 16-byte boundaries: pad the rows
+            # once (one read + one write of the volume) and hand the strides over; TMA zero-fills beyond the logical X.
+            ixp = (ix + 3) // 4 * 4
+            padded = torch.empty((iz, iy, ixp), dtype=torch.float32, device=vol.device)
+            padded[:, :, :ix].copy_(vol)
+            code = _cabi.lib().shrimpy_affine_strided_device(
+                padded.data_ptr(), out.data_ptr(), iz, iy, ix, iy * ixp, ixp, *shape, Mp, float(cval),
+                int(bool(nan_to_zero)), stream)
+            if code == _cabi.OK:
+                return out
+            if "not eligible" not in _cabi.lib().shrimpy_last_error().decode("utf-8", "replace"):
+                _cabi.check(code)
         _cabi.check(_cabi.lib().shrimpy_affine_device(
-            vol.data_ptr(), out.data_ptr(), *vol.shape, *shape,
-            M.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), float(cval), int(bool(nan_to_zero)),
-            torch.cuda.current_stream().cuda_stream))
+            vol.data_ptr(), out.data_ptr(), iz, iy, ix, *shape, Mp, float(cval), int(bool(nan_to_zero)), stream))
     return out
 
 

@@ -285,6 +285,32 @@ def test_tilt_kernel_nan_to_num(env, monkeypatch):
     assert np.array_equal(got == 0.0, want == 0.0)
 
 
+@pytest.mark.parametrize("which", ["in_plane_90", "small_rotations"])
+def test_odd_row_length_goes_through_padded_rows(env, which, monkeypatch):
+    """X not a multiple of 4 (e.g. a deskewed (.., 1279) volume as the INPUT of a registration): the Python layer pads
+    the rows once and the plane-streaming kernels read through the strided tensor map (TMA zero-fills beyond the logical
+    X).  Same voxels as scipy, same padded set, and the same as the dense-only kernels within the lerp tolerance."""
+    torch, register, _, c = env
+    rng = np.random.default_rng(41)
+    vol = rng.standard_normal((40, 300, 353)).astype(np.float32)          # 4.2 M voxels, X = 353
+    if which == "in_plane_90":
+        M = np.array([[0.9, 0, 0, 1.5], [0, 0, -1.1, 298.0], [0, 1.1, 0, 2.0], [0, 0, 0, 1.0]])
+        shape = (38, 300, 280)
+    else:
+        M = np.array(TILT_CASES["small_rotations"][0] + [[0, 0, 0, 1.0]])
+        shape = (40, 300, 353)
+    want = c.apply_affine_transform(vol, M, shape, cval=-4.0)
+    monkeypatch.setenv("SHRIMPY_AFFINE_KERNEL", "s!" if which == "in_plane_90" else "m!")   # a fallback would be an error
+    got = _run(env, vol, M, shape, cval=-4.0)
+    assert_close_range(got, want, AFFINE_TOL, f"padded rows {which}")
+    assert np.array_equal(got == -4.0, want == -4.0)
+    monkeypatch.delenv("SHRIMPY_AFFINE_KERNEL")
+    monkeypatch.setattr(register, "_PAD_MIN_VOXELS", 1 << 62)          # dense-only kernels on the unpadded array
+    dense = _run(env, vol, M, shape, cval=-4.0)
+    assert np.array_equal(dense == -4.0, got == -4.0)
+    assert_close_range(dense, got, AFFINE_TOL, "dense vs padded")
+
+
 def test_medium_volume_vs_c_oracle(env):
     _, _, _, c = env
     rng = np.random.default_rng(8)

@@ -200,6 +200,17 @@ def test_config3_full_size(env):
         assert torch.equal(got == -9.0, ~inside), f"{name}: padded-voxel set differs"
         del out
 
+    # the reverse direction: a deskewed-grid volume (X = 1279, not a multiple of 4) onto the label-free grid
+    back = torch.randn((100, 2048, 1279), device="cuda", generator=gen)
+    Minv = np.linalg.inv(M90t)
+    out = register.affine_transform_zyx(back, Minv, (107, 2048, 2048), cval=-9.0)
+    o, want, inside = _sample_affine(torch, back, Minv, (107, 2048, 2048), -9.0, 400_000, seed=77)
+    got = out[o[0], o[1], o[2]].to(torch.float64)
+    err = float((got - want).abs().max())
+    assert err <= AFFINE_TOL * float(want.max() - want.min()), f"odd X: max|err| {err:.3e}"
+    assert torch.equal(got == -9.0, ~inside), "odd X: padded-voxel set differs"
+    del out, back
+
     # identity and integer shifts are exact copies
     assert torch.equal(register.affine_transform_zyx(vol, np.eye(4), shape), vol)
     Ms = np.eye(4)

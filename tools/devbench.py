@@ -120,6 +120,25 @@ if __name__ == "__main__":
             print(json.dumps(dict(case=name, out=oshape, ms=round(ms, 4), gbs_alg=round(nbytes / ms / 1e6, 1),
                                   frac=round(nbytes / ms / 1e6 / PEAK, 3), gvox_out=round(out.numel() / ms / 1e6, 1),
                                   inside=round(inside, 3))), flush=True)
+    if "affodd" in args.cases:
+        from shrimpy_b200 import register
+        vol = torch.randn((100, 2048, 1279), device="cuda")
+        M90t = np.array([[1.0, 0.02, -0.015, 3.5], [0.03, 0, -1.288, 2040.0], [-0.02, 1.288, 0, -20.0], [0, 0, 0, 1]])
+        M90 = np.array([[1.0, 0, 0, 3.5], [0, 0, -1.288, 2040.0], [0, 1.288, 0, -20.0], [0, 0, 0, 1]])
+        for name, M in (("odd_x_rot90_inverse", np.linalg.inv(M90)), ("odd_x_rot90tilt_inverse", np.linalg.inv(M90t))):
+            out = torch.empty((107, 2048, 2048), device="cuda")
+            for pad in (True, False):
+                register._PAD_MIN_VOXELS = (1 << 22) if pad else (1 << 62)
+                for _ in range(2):
+                    register.affine_transform_zyx(vol, M, out.shape, out=out)
+                torch.cuda.synchronize()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                for _ in range(5):
+                    register.affine_transform_zyx(vol, M, out.shape, out=out)
+                b.record(); torch.cuda.synchronize()
+                print(json.dumps(dict(case=name, padded_rows=pad, ms=round(a.elapsed_time(b) / 5, 4))), flush=True)
+        register._PAD_MIN_VOXELS = 1 << 22
     if "afftile" in args.cases:
         from shrimpy_b200 import register
         shape = (107, 2048, 2048)
