@@ -267,7 +267,7 @@ __global__ void __launch_bounds__(tilt_threads(SWAP), (IA * RB <= 4) ? 3 : 2)
     // a + 2R, ... (R = consumers / LB), so its shared offset and global pointer are set up once and only stepped.
     constexpr int kDrainRows = kTiltConsumers / LB, kDrainIters = LA / kDrainRows;
     const int drain_a = tid / LB, drain_b = tid % LB;
-    const bool drain_full = t0y + TY <= P.oy && t0x + TX <= P.ox;
+    const bool drain_full = tile_full;
     const bool drain_col_ok = t0x + drain_b < P.ox;
     float *pdrain = pstep + (long long)(t0y + drain_a) * P.ox + t0x + drain_b;
     const long long drain_stride = (long long)kDrainRows * P.ox;
