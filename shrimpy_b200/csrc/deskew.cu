@@ -260,19 +260,25 @@ __device__ __forceinline__ void fast_scaled(const uint8_t *tile, const uint32_t 
             const float4 v = *reinterpret_cast<const float4 *>(g + k * g_row_stride + j);
             gk[j] = v.x; gk[j + 1] = v.y; gk[j + 2] = v.z; gk[j + 3] = v.w;
         }
+        // packed pairs (FADD2 / FFMA2): the same operations and rounding per element as the scalar sequence
 #pragma unroll
-        for (int j = 0; j < EPC; ++j) {
-            float a, d;
+        for (int j = 0; j < EPC; j += 2) {
+            float2 a2, d2;
             if (sizeof(T) == 2) {
-                const uint32_t am = Chunk<uint16_t>::magic(A, j), bm = Chunk<uint16_t>::magic(B, j);
-                d = __uint_as_float(bm) - __uint_as_float(am);
-                a = __uint_as_float(am) - 8388608.0f;
+                const float2 am = make_float2(__uint_as_float(Chunk<uint16_t>::magic(A, j)), __uint_as_float(Chunk<uint16_t>::magic(A, j + 1)));
+                const float2 bm = make_float2(__uint_as_float(Chunk<uint16_t>::magic(B, j)), __uint_as_float(Chunk<uint16_t>::magic(B, j + 1)));
+                d2 = __fadd2_rn(bm, make_float2(-am.x, -am.y));
+                a2 = __fadd2_rn(am, make_float2(-8388608.0f, -8388608.0f));
             } else {
-                a = Chunk<float>::get(A, j);
-                d = Chunk<float>::get(B, j) - a;
+                a2 = make_float2(Chunk<float>::get(A, j), Chunk<float>::get(A, j + 1));
+                const float2 b2 = make_float2(Chunk<float>::get(B, j), Chunk<float>::get(B, j + 1));
+                d2 = __fadd2_rn(b2, make_float2(-a2.x, -a2.y));
             }
-            const float t = fmaf(w[k], d, a);
-            out[j] = (k == 0) ? gk[j] * t : fmaf(gk[j], t, out[j]);
+            const float2 t2 = __ffma2_rn(make_float2(w[k], w[k]), d2, a2);
+            const float2 g2 = make_float2(gk[j], gk[j + 1]);
+            const float2 r2 = (k == 0) ? __fmul2_rn(g2, t2) : __ffma2_rn(g2, t2, make_float2(out[j], out[j + 1]));
+            out[j] = r2.x;
+            out[j + 1] = r2.y;
         }
     }
 }
