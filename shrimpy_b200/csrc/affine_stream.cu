@@ -430,8 +430,10 @@ int launch_affine_stream(AffineParams P, int nan_to_zero, cudaStream_t s, bool *
             if (bytes > budget) continue;
             // cost: staged elements per output voxel; deeper rings and more columns per thread are preferred
             // (measured on config 3: with lanes along o1, 256-byte drained rows beat 128-byte ones by 5 %)
+            // and with lanes along o2, 4 columns per thread at 3 CTAs per SM and 512-byte rows beat the rest by 3-4 %)
             const double cost = (double)(BY * BX) / (TY * TX) + (rl == 2 ? 0.15 : 0.0) + (IA * RB < 8 ? 0.05 : 0.0) -
-                                (swap && LB >= 64 ? 0.25 : 0.0);
+                                (swap && LB >= 64 ? 0.25 : 0.0) + (!swap && IA * RB == 8 ? 0.25 : 0.0) -
+                                (!swap && LA >= 128 ? 0.1 : 0.0);
             if (cost < best) {
                 best = cost; bIA = IA; bRB = RB; bring = rl;
                 P.BY = (int)BY; P.BX = (int)BX; P.pitch = (int)BX; P.PB = (int)PB; P.BZ = 1;
