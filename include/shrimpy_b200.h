@@ -206,6 +206,23 @@ int shrimpy_deskew_host(shrimpy_pipeline *p, const void *h_raw, int raw_dtype, f
 /* counters of the last shrimpy_deskew_host call: kernels launched, H2D / D2H bytes */
 int shrimpy_pipeline_stats(const shrimpy_pipeline *p, int64_t *launches, int64_t *h2d_bytes, int64_t *d2h_bytes);
 
+/*
+ * Blosc-1 frame codec for the OME-Zarr chunk loader (host memory only; no CUDA call).  The reference acquires with
+ * compression="blosc-zstd" inside zarr-v3 shards (shrimpy/mantis/mantis_engine.py:474-481; asserted by
+ * shrimpy/tests/test_mantis_integration.py:182-188), so streaming its stores means undoing blosc's framing
+ * (16-byte header, block table, per-block split streams, byte/bit shuffle) around zstd / lz4 / zlib streams.
+ * The stream codecs are taken from the system's runtime libraries via dlopen.  shrimpy_blosc_decode writes exactly
+ * dst_bytes (= the frame's nbytes) into dst, decoding blocks on up to `threads` threads; it may be called
+ * concurrently from many threads.  shrimpy_blosc_encode writes one frame (codec: 1 lz4, 3 zlib, 4 zstd; shuffle:
+ * 0 none, 1 byte, 2 bit; blocksize 0 = 256 KiB; split != 0 = one stream per byte plane where blosc's rule allows).
+ */
+int shrimpy_blosc_info(const void *frame, size_t frame_bytes, int64_t *nbytes, int64_t *cbytes, int32_t *blocksize,
+                       int32_t *typesize, int32_t *flags);
+int shrimpy_blosc_decode(const void *frame, size_t frame_bytes, void *dst, size_t dst_bytes, int threads);
+size_t shrimpy_blosc_encode_bound(size_t nbytes, int32_t blocksize, int typesize);
+int shrimpy_blosc_encode(const void *data, size_t nbytes, int typesize, int codec, int level, int shuffle,
+                         int32_t blocksize, int split, void *frame, size_t frame_capacity, size_t *frame_bytes);
+
 /* Number of kernel launches issued by this library in this process (all entry points). */
 int64_t shrimpy_launch_count(void);
 

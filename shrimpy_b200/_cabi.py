@@ -42,6 +42,10 @@ EXPORTS = (
     "shrimpy_pipeline_destroy",
     "shrimpy_deskew_host",
     "shrimpy_pipeline_stats",
+    "shrimpy_blosc_info",
+    "shrimpy_blosc_decode",
+    "shrimpy_blosc_encode_bound",
+    "shrimpy_blosc_encode",
     "shrimpy_launch_count",
 )
 
@@ -124,6 +128,17 @@ def _declare(lib) -> None:
                                         c_dbl, c_dbl, c_dbl, c_flt]
     lib.shrimpy_pipeline_stats.restype = c_int
     lib.shrimpy_pipeline_stats.argtypes = [c_vp, ctypes.POINTER(c_i64), ctypes.POINTER(c_i64), ctypes.POINTER(c_i64)]
+    c_sz, c_i32 = ctypes.c_size_t, ctypes.c_int32
+    lib.shrimpy_blosc_info.restype = c_int
+    lib.shrimpy_blosc_info.argtypes = [c_vp, c_sz, ctypes.POINTER(c_i64), ctypes.POINTER(c_i64), ctypes.POINTER(c_i32),
+                                       ctypes.POINTER(c_i32), ctypes.POINTER(c_i32)]
+    lib.shrimpy_blosc_decode.restype = c_int
+    lib.shrimpy_blosc_decode.argtypes = [c_vp, c_sz, c_vp, c_sz, c_int]
+    lib.shrimpy_blosc_encode_bound.restype = c_sz
+    lib.shrimpy_blosc_encode_bound.argtypes = [c_sz, c_i32, c_int]
+    lib.shrimpy_blosc_encode.restype = c_int
+    lib.shrimpy_blosc_encode.argtypes = [c_vp, c_sz, c_int, c_int, c_int, c_int, c_i32, c_int, c_vp, c_sz,
+                                         ctypes.POINTER(c_sz)]
 
 
 def lib():

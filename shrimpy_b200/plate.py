@@ -71,16 +71,21 @@ def list_units(positions: Sequence[Position]) -> List[Tuple[int, int, int]]:
 
 
 def create_deskewed_plate(path, src: Sequence[Position], settings: DeskewSettings, z_chunk: int = 50,
-                          zstd_level: Optional[int] = None) -> List[Position]:
+                          zstd_level: Optional[int] = None, blosc: Optional[dict] = None,
+                          shard_z: Optional[int] = None) -> List[Position]:
     """Output plate mirroring ``src``: float32, deskewed shape, chunks ``(1, 1, z_chunk, Y', X')`` and the scale
-    transform ``(1, 1) + voxel_size`` exactly as ``scripts/measure_psf.py:273-287`` writes it."""
+    transform ``(1, 1) + voxel_size`` exactly as ``scripts/measure_psf.py:273-287`` writes it.  ``blosc`` /
+    ``shard_z`` (z extent of one shard file, a multiple of ``z_chunk``) select the acquisition's own storage layout
+    (``sharding_indexed`` -> ``blosc``; ``shrimpy/mantis/mantis_engine.py:474-481``)."""
     T, C, Z, Y, X = src[0].array.shape
     g = deskew_geometry((Z, Y, X), settings.ls_angle_deg, settings.px_to_scan_ratio, settings.keep_overhang,
                         settings.average_n_slices, settings.pixel_size_um)
     Zd, Yd, Xd = g.out_shape
-    return create_plate(path, [p.name for p in src], (T, C, Zd, Yd, Xd), (1, 1, min(z_chunk, Zd), Yd, Xd), np.float32,
+    zc = min(z_chunk, Zd)
+    shard = None if shard_z is None else (1, 1, zc * max(1, -(-min(shard_z, Zd) // zc)), Yd, Xd)
+    return create_plate(path, [p.name for p in src], (T, C, Zd, Yd, Xd), shard or (1, 1, zc, Yd, Xd), np.float32,
                         channel_names=src[0].channel_names, scale=(1.0, 1.0) + tuple(float(v) for v in g.voxel_size),
-                        zstd_level=zstd_level)
+                        zstd_level=zstd_level, blosc=blosc, shard_inner=(1, 1, zc, Yd, Xd) if shard else None)
 
 
 def deskew_plate(src: Sequence[Position], settings, dst: Optional[Sequence[Position]] = None, *, rank: int = 0,

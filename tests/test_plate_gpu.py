@@ -8,15 +8,21 @@ from helpers import TIGHT_TOL, assert_close_range, synthetic_stack
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture()
-def small_plate(tmp_path):
+@pytest.fixture(params=["zstd", "acquisition"])
+def small_plate(tmp_path, request):
+    """``acquisition``: the reference's own storage layout -- blosc(zstd, shuffle) inside sharding_indexed shards
+    (shrimpy/mantis/mantis_engine.py:474-481), 40 slices in shards of 32 with inner chunks of 8."""
     from shrimpy_b200 import zarr_io
 
     names = ["A/1/fov0", "A/2/fov0", "B/1/fov0"]
     shape = (2, 2, 40, 12, 64)
-    positions = zarr_io.create_plate(tmp_path / "raw.zarr", names, shape, (1, 1, 16, 12, 64), np.uint16,
-                                     channel_names=["BF", "GFP"], scale=(1, 1, 0.3, 0.116, 0.116),
-                                     zstd_level=3 if zarr_io.zstd_available() else None)
+    if request.param == "acquisition":
+        layout = dict(chunks=(1, 1, 32, 12, 64), blosc={"cname": "zstd", "clevel": 1, "shuffle": "shuffle"},
+                      shard_inner=(1, 1, 8, 12, 64))
+    else:
+        layout = dict(chunks=(1, 1, 16, 12, 64), zstd_level=3 if zarr_io.zstd_available() else None)
+    positions = zarr_io.create_plate(tmp_path / "raw.zarr", names, shape, layout.pop("chunks"), np.uint16,
+                                     channel_names=["BF", "GFP"], scale=(1, 1, 0.3, 0.116, 0.116), **layout)
     truth = {}
     for i, pos in enumerate(positions):
         for t in range(2):
@@ -36,7 +42,10 @@ def test_plate_streaming_matches_oracle(small_plate):
     src = zarr_io.open_plate(root / "raw.zarr")
     settings = DeskewSettings(ls_angle_deg=30.0, pixel_size_um=0.116, scan_step_um=0.3, keep_overhang=False,
                               average_n_slices=3)
-    dst = plate.create_deskewed_plate(root / "deskewed.zarr", src, settings, z_chunk=3)
+    sharded = src[0].array.shard_inner is not None           # write back in the layout the plate came in
+    dst = plate.create_deskewed_plate(root / "deskewed.zarr", src, settings, z_chunk=3,
+                                      blosc={"cname": "zstd", "clevel": 1, "shuffle": "shuffle"} if sharded else None,
+                                      shard_z=6 if sharded else None)
     seen = []
     stats = plate.deskew_plate(src, settings, dst, depth=3, io_threads=3,
                                on_result=lambda name, t, c, arr: seen.append((name, t, c, float(arr.sum()))))

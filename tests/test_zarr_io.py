@@ -58,11 +58,13 @@ def test_missing_chunk_reads_fill_value_and_bad_buffers_raise(tmp_path):
 def test_unsupported_codecs_are_named(tmp_path):
     arr = zarr_io.ZarrArray.create(tmp_path / "a", (1, 1, 4, 4, 4), (1, 1, 4, 4, 4), np.uint16)
     meta = json.loads((tmp_path / "a" / "zarr.json").read_text())
-    meta["codecs"] = [{"name": "bytes", "configuration": {"endian": "little"}},
-                      {"name": "blosc", "configuration": {"cname": "zstd", "clevel": 1, "shuffle": "shuffle"}}]
-    (tmp_path / "a" / "zarr.json").write_text(json.dumps(meta))
-    with pytest.raises(NotImplementedError, match="blosc"):
-        zarr_io.ZarrArray.open(tmp_path / "a")
+    for tail, word in (({"name": "gzip", "configuration": {"level": 5}}, "gzip"),
+                       ({"name": "blosc", "configuration": {"cname": "blosclz", "clevel": 1, "shuffle": "shuffle"}}, "blosclz"),
+                       ({"name": "blosc", "configuration": {"cname": "snappy", "clevel": 1, "shuffle": "shuffle"}}, "snappy")):
+        meta["codecs"] = [{"name": "bytes", "configuration": {"endian": "little"}}, tail]
+        (tmp_path / "a" / "zarr.json").write_text(json.dumps(meta))
+        with pytest.raises(NotImplementedError, match=word):
+            zarr_io.ZarrArray.open(tmp_path / "a")
 
 
 @pytest.mark.parametrize("index_at_end", [True, False])

@@ -33,6 +33,10 @@ def main():
     ap.add_argument("--io-threads", type=int, default=6)
     ap.add_argument("--write", type=int, default=0, help="1: also write the deskewed plate back to the store")
     ap.add_argument("--zstd", type=int, default=-1)
+    ap.add_argument("--blosc", default="", help="cname (zstd | lz4): write the raw plate as blosc(cname, clevel 1, shuffle) "
+                    "inside shards, the acquisition's own layout (mantis_engine.py:474-481)")
+    ap.add_argument("--inner-z", type=int, default=50, help="z extent of the inner chunks of a shard (with --blosc)")
+    ap.add_argument("--camera-like", type=int, default=0, help="1: shot-noise frames (compress ~2.3x) instead of uniform noise")
     ap.add_argument("--out-z-chunk", type=int, default=10)
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -49,15 +53,26 @@ def main():
     root = Path(args.root) / f"rank{rank}"
     shutil.rmtree(root, ignore_errors=True)
     names = [f"{'ABCDEFGH'[i // 12]}/{i % 12 + 1}/fov0" for i in range(args.positions)]
-    src = zarr_io.create_plate(root / "raw.zarr", names, (args.timepoints, 1, Z, Y, X), (1, 1, min(512, Z), Y, X),
-                               np.uint16, channel_names=["GFP"], zstd_level=None if args.zstd < 0 else args.zstd)
+    zc = min(512, Z)
+    blosc = {"cname": args.blosc, "clevel": 1, "shuffle": "shuffle"} if args.blosc else None
+    inner = (1, 1, min(args.inner_z, zc), Y, X) if blosc else None
+    if inner is not None:
+        zc = -(-zc // inner[2]) * inner[2]
+    src = zarr_io.create_plate(root / "raw.zarr", names, (args.timepoints, 1, Z, Y, X), (1, 1, zc, Y, X),
+                               np.uint16, channel_names=["GFP"], zstd_level=None if args.zstd < 0 else args.zstd,
+                               blosc=blosc, shard_inner=inner)
     rng = np.random.default_rng(rank)
-    stack = rng.integers(100, 60000, size=(Z, Y, X), dtype=np.uint16)
+    if args.camera_like:
+        stack = (400 + rng.poisson(120, size=(Z, Y, X))).astype(np.uint16)
+    else:
+        stack = rng.integers(100, 60000, size=(Z, Y, X), dtype=np.uint16)
     t0 = time.perf_counter()
-    for pos in src:
-        for t in range(args.timepoints):
-            pos.array.write_stack(t, 0, stack)
-            stack[0, 0, :8] += 1
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max(1, args.io_threads)) as wpool:
+        for pos in src:
+            for t in range(args.timepoints):
+                pos.array.write_stack(t, 0, stack, pool=wpool)
+                stack[0, 0, :8] += 1
     gen_s = time.perf_counter() - t0
     settings = DeskewSettings(ls_angle_deg=30.0, pixel_size_um=0.116, px_to_scan_ratio=0.39, keep_overhang=False,
                               average_n_slices=3)
@@ -74,7 +89,10 @@ def main():
     if rank == 0:
         d = stats.as_dict()
         print(json.dumps({"config": f"plate stream: {args.positions} pos x {args.timepoints} t x ({Z},{Y},{X}) uint16 per rank",
-                          "n_gpus": world, "store": str(args.root), "write_back": bool(args.write),
+                          "n_gpus": world, "store": str(args.root),
+                          "codec": (f"sharding_indexed(inner z {inner[2]}) -> blosc({args.blosc}, clevel 1, shuffle)" if blosc else
+                                    ("zstd" if args.zstd >= 0 else "bytes")), "camera_like": bool(args.camera_like),
+                          "write_back": bool(args.write),
                           "job_gvoxel_out_per_s": round(float(vox.item()) / float(secs.item()) / 1e9, 2),
                           "rank0": {k: (round(v, 3) if isinstance(v, float) else v) for k, v in d.items()},
                           "plate_write_s": round(gen_s, 2)}), flush=True)
