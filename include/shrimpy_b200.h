@@ -184,6 +184,10 @@ int shrimpy_minmax_device(const float *d_data, int64_t count, float *d_out2, voi
 int shrimpy_hist256_device(const float *d_data, int64_t count, float vmin, float vmax, uint64_t *d_hist, void *stream);
 int shrimpy_center_of_mass_device(const float *d_data, int Z, int Y, int X, float background, double *d_sums4,
                                   void *stream);
+/* Z max-projection of the background-filtered volume, d_out[y][x] = max_z max(v - background, 0): the image the
+ * tracker saves next to the centroid (shrimpy/dynatrack/tracking.py:1447-1455). */
+int shrimpy_zmax_projection_device(const float *d_data, int Z, int Y, int X, float background, float *d_out,
+                                   void *stream);
 
 /* min over a device array (for cval = min(raw), the scipy-generation default). */
 int shrimpy_min_device(const void *d_raw, int raw_dtype, int64_t count, float *d_result, void *stream);

@@ -37,6 +37,7 @@ EXPORTS = (
     "shrimpy_minmax_device",
     "shrimpy_hist256_device",
     "shrimpy_center_of_mass_device",
+    "shrimpy_zmax_projection_device",
     "shrimpy_min_device",
     "shrimpy_pipeline_create",
     "shrimpy_pipeline_destroy",
@@ -117,6 +118,8 @@ def _declare(lib) -> None:
     lib.shrimpy_hist256_device.argtypes = [c_vp, c_i64, c_flt, c_flt, c_vp, c_vp]
     lib.shrimpy_center_of_mass_device.restype = c_int
     lib.shrimpy_center_of_mass_device.argtypes = [c_vp, c_int, c_int, c_int, c_flt, c_vp, c_vp]
+    lib.shrimpy_zmax_projection_device.restype = c_int
+    lib.shrimpy_zmax_projection_device.argtypes = [c_vp, c_int, c_int, c_int, c_flt, c_vp, c_vp]
     lib.shrimpy_min_device.restype = c_int
     lib.shrimpy_min_device.argtypes = [c_vp, c_int, c_i64, c_vp, c_vp]
     lib.shrimpy_pipeline_create.restype = c_int

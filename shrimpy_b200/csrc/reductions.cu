@@ -137,6 +137,42 @@ __global__ void __launch_bounds__(256) com_kernel(const float *__restrict__ v, i
     }
 }
 
+// Z max-projection of the background-filtered volume, out[i] = max_z max(v[z][i] - background, 0) over the flattened
+// (Y, X) plane (tracking.py:1447-1455: `(img - background).clamp_min(0).amax(dim=0)`).  VEC floats per thread, eight
+// planes in flight; max is order-independent, so the result equals torch's bit for bit.
+template <int VEC>
+__global__ void __launch_bounds__(256) zmax_kernel(const float *__restrict__ v, int Z, long long plane, float background,
+                                                   float *__restrict__ out) {
+    const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * VEC;
+    if (i >= plane) return;
+    float best[VEC];
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) best[k] = 0.f;
+    auto take = [&](const float *p) {
+        if (VEC == 4) {
+            const float4 a = __ldg(reinterpret_cast<const float4 *>(p));
+            best[0] = fmaxf(best[0], a.x - background);
+            best[1 % VEC] = fmaxf(best[1 % VEC], a.y - background);
+            best[2 % VEC] = fmaxf(best[2 % VEC], a.z - background);
+            best[3 % VEC] = fmaxf(best[3 % VEC], a.w - background);
+        } else {
+            best[0] = fmaxf(best[0], __ldg(p) - background);
+        }
+    };
+    const float *col = v + i;
+    int z = 0;
+    for (; z + 8 <= Z; z += 8) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) take(col + (long long)(z + k) * plane);
+    }
+    for (; z < Z; ++z) take(col + (long long)z * plane);
+    if (VEC == 4) {
+        *reinterpret_cast<float4 *>(out + i) = make_float4(best[0], best[1 % VEC], best[2 % VEC], best[3 % VEC]);
+    } else {
+        out[i] = best[0];
+    }
+}
+
 }  // namespace shrimpy
 
 using namespace shrimpy;
@@ -180,6 +216,21 @@ extern "C" int shrimpy_center_of_mass_device(const float *d_data, int Z, int Y, 
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     SHRIMPY_CUDA_TRY(cudaMemsetAsync(d_sums4, 0, 4 * sizeof(double), s));
     com_kernel<<<grid_for((long long)Z * Y, 8 * 4), 256, 0, s>>>(d_data, Z, Y, X, background, d_sums4);
+    count_launch();
+    SHRIMPY_CUDA_TRY(cudaGetLastError());
+    return SHRIMPY_OK;
+}
+
+extern "C" int shrimpy_zmax_projection_device(const float *d_data, int Z, int Y, int X, float background, float *d_out,
+                                              void *stream) {
+    if (!d_data || !d_out || Z <= 0 || Y <= 0 || X <= 0) return fail(SHRIMPY_EINVAL, "zmax_projection: bad arguments");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const long long plane = (long long)Y * X;
+    const bool vec = plane % 4 == 0 && ((reinterpret_cast<uintptr_t>(d_data) | reinterpret_cast<uintptr_t>(d_out)) & 15u) == 0;
+    if (vec)
+        zmax_kernel<4><<<(unsigned)((plane / 4 + 255) / 256), 256, 0, s>>>(d_data, Z, plane, background, d_out);
+    else
+        zmax_kernel<1><<<(unsigned)((plane + 255) / 256), 256, 0, s>>>(d_data, Z, plane, background, d_out);
     count_launch();
     SHRIMPY_CUDA_TRY(cudaGetLastError());
     return SHRIMPY_OK;

@@ -4,6 +4,9 @@
 * ``_percentile(img, percentile, nbins=256)``              -- ``shrimpy/dynatrack/tracking.py:572-595``
 * ``_intensity_center_of_mass(img, background=0.0)``       -- ``shrimpy/dynatrack/tracking.py:598-649``
 
+and the projection the tracker saves beside the centroid, ``(img - background).clamp_min(0).amax(dim=0)``
+(``tracking.py:1447-1455``) -- ``max_projection``.
+
 The reference makes ~10 full passes over the volume for the pair (min, max, histc, a float32 copy, subtract,
 clamp, sum and three marginal sums); here it is three streaming passes (range, histogram, weighted sums),
 each an HBM-bound kernel behind the C-ABI.  No CPU fallback.
@@ -15,7 +18,7 @@ import numpy as np
 
 from . import _cabi
 
-__all__ = ["value_range", "percentile", "intensity_center_of_mass"]
+__all__ = ["value_range", "percentile", "intensity_center_of_mass", "max_projection"]
 
 
 def _f32_cuda(img):
@@ -81,3 +84,18 @@ def intensity_center_of_mass(img, background: float = 0.0):
     if total <= 0:
         return torch.tensor([(s - 1) / 2.0 for s in v.shape], device=v.device, dtype=torch.float32)
     return torch.tensor([sz / total, sy / total, sx / total], device=v.device, dtype=torch.float32)
+
+
+def max_projection(img, background: float = 0.0):
+    """``(img - background).clamp_min(0).amax(dim=0)`` of a ``(Z, Y, X)`` CUDA volume in one pass (bit-identical to the
+    torch expression for finite data: the subtraction is the same float32 operation and the maximum does not depend
+    on order; NaN voxels are skipped rather than propagated)."""
+    torch, v = _f32_cuda(img)
+    if v.dim() != 3:
+        raise ValueError(f"expected a (Z, Y, X) volume, got {tuple(v.shape)}")
+    Z, Y, X = v.shape
+    with torch.cuda.device(v.device):
+        out = torch.empty((Y, X), dtype=torch.float32, device=v.device)
+        _cabi.check(_cabi.lib().shrimpy_zmax_projection_device(v.data_ptr(), Z, Y, X, float(background), out.data_ptr(),
+                                                               torch.cuda.current_stream().cuda_stream))
+    return out

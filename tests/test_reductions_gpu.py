@@ -99,3 +99,22 @@ def test_value_range_fused_into_the_deskew(n, keep, dtype):
         fused = sb.deskew_zyx(raw, 30.0, 0.39, keep, n, cval=-5.0, value_range=rng, scale=scale)
         assert torch.equal(fused, flatfield.deskew_flat_field_zyx(raw, 30.0, 0.39, keep, n, cval=-5.0, scale=scale))
         assert rng.tolist() == [float(fused.min()), float(fused.max())]
+
+
+@pytest.mark.parametrize("shape", [(100, 64, 1279), (37, 50, 128), (1, 3, 5), (9, 1, 4)])
+def test_max_projection_equals_the_torch_expression(shape):
+    """tracking.py:1447-1455: ``(img - background).clamp_min(0).amax(dim=0)``; vector path (Y*X % 4 == 0) and scalar."""
+    import torch
+
+    from shrimpy_b200 import reductions as red
+
+    vol = torch.from_numpy(_volume(11, shape)).cuda()
+    for bg in (0.0, 412.5, 1e9):
+        want = (vol - bg).clamp_min(0).amax(dim=0)
+        got = red.max_projection(vol, bg)
+        assert got.shape == want.shape and got.dtype == torch.float32
+        assert torch.equal(got, want), (shape, bg)
+    view = vol[:, :, 1:]                                             # a non-contiguous view is made contiguous first
+    assert torch.equal(red.max_projection(view, 100.0), (view - 100.0).clamp_min(0).amax(dim=0))
+    with pytest.raises(ValueError):
+        red.max_projection(vol[0])
