@@ -107,7 +107,18 @@ extern "C" int shrimpy_deskew_host(shrimpy_pipeline *p, const void *h_raw, int r
     size_t ps_budget = p->budget / (kBuf * (raw_per_p + out_per_p));
     if (ps_budget == 0) ps_budget = 1;
     int ps = (int)std::min<size_t>(ps_budget, (size_t)std::max(1, (Yn + 11) / 12));
-    const int n_slabs = (Yn + ps - 1) / ps;
+    // The D2H stream is the bottleneck stage and runs without gaps once it has started, so what the call pays on top
+    // is the fill: the first slab's H2D + kernel, with nothing to overlap.  Slabs therefore ramp up 1, 2, 4, ... tilt
+    // blocks before reaching the steady size.
+    std::vector<int> starts, counts;
+    for (int p0 = 0, ramp = 1; p0 < Yn; ramp *= 2) {
+        const int pc = std::min(std::min(ramp, ps), Yn - p0);
+        starts.push_back(p0);
+        counts.push_back(pc);
+        p0 += pc;
+        if (ramp > ps) ramp = ps;
+    }
+    const int n_slabs = (int)starts.size();
 
     const size_t raw_need = (size_t)ps * raw_per_p, out_need = (size_t)ps * out_per_p;
     if (raw_need > p->raw_cap || out_need > p->out_cap) {
@@ -124,7 +135,7 @@ extern "C" int shrimpy_deskew_host(shrimpy_pipeline *p, const void *h_raw, int r
     const size_t src_pitch = (size_t)Y * X * es;  // one scan slice of the host stack
     for (int i = 0; i < n_slabs; ++i) {
         const int b = i % kBuf;
-        const int p0 = i * ps, pc = std::min(ps, Yn - p0);
+        const int p0 = starts[i], pc = counts[i];
         int32_t yr[2], zr[2];
         int rc = shrimpy_deskew_window_needs(Z, Y, n_avg, m00, m02, shift, p0, pc, 0, Xp, yr, zr);
         if (rc) return rc;
