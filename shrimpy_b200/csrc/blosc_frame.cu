@@ -31,6 +31,7 @@
 #include <atomic>
 #include <cstring>
 #include <mutex>
+#include <new>
 #include <thread>
 #include <vector>
 
@@ -304,7 +305,14 @@ extern "C" int shrimpy_blosc_decode(const void *frame, size_t frame_bytes, void 
     char message[kErrLen] = {0};
     std::mutex message_lock;
     auto run = [&] {
-        std::vector<uint8_t> tmp((size_t)f.blocksize);
+        std::vector<uint8_t> tmp;
+        try {
+            tmp.resize((size_t)std::min(f.blocksize, f.nbytes));        // a block never exceeds the frame
+        } catch (const std::bad_alloc &) {
+            std::lock_guard<std::mutex> g(message_lock);
+            if (status.exchange(SHRIMPY_ENOMEM) == SHRIMPY_OK) snprintf(message, kErrLen, "blosc: no memory for a %d-byte block", f.blocksize);
+            return;
+        }
         for (int32_t b; (b = next.fetch_add(1)) < f.nblocks && status.load() == SHRIMPY_OK;)
             if (int rc = decode_block(f, src, b, (uint8_t *)dst, tmp.data())) {
                 std::lock_guard<std::mutex> g(message_lock);       // last_error is thread-local: carry it to the caller
@@ -312,7 +320,13 @@ extern "C" int shrimpy_blosc_decode(const void *frame, size_t frame_bytes, void 
             }
     };
     std::vector<std::thread> pool;
-    for (int t = 1; t < workers; ++t) pool.emplace_back(run);
+    for (int t = 1; t < workers; ++t) {
+        try {
+            pool.emplace_back(run);
+        } catch (const std::exception &) {
+            break;                                                      // no more threads: the ones we have do the work
+        }
+    }
     run();
     for (auto &t : pool) t.join();
     if (status.load() != SHRIMPY_OK) return fail(status.load(), "%s", message);
@@ -350,7 +364,12 @@ extern "C" int shrimpy_blosc_encode(const void *data, size_t nbytes, int typesiz
     out[0] = 2; out[1] = 1; out[3] = (uint8_t)typesize;
     wr32(out + 4, f.nbytes); wr32(out + 8, blocksize);
     size_t pos = (size_t)kHeader + 4 * (size_t)f.nblocks;
-    std::vector<uint8_t> tmp((size_t)blocksize);
+    std::vector<uint8_t> tmp;
+    try {
+        tmp.resize((size_t)blocksize);
+    } catch (const std::bad_alloc &) {
+        return fail(SHRIMPY_ENOMEM, "blosc: no memory for a %d-byte block", blocksize);
+    }
     bool gave_up = false;
     for (int32_t b = 0; b < f.nblocks && !gave_up; ++b) {
         const bool last = b == f.nblocks - 1;

@@ -252,3 +252,29 @@ def test_unsharded_blosc_chunks_and_crc32c_vector(tmp_path):
     zarr_io.ZarrArray.open(tmp_path / "b").read_stack_into(0, 0, out)
     assert np.array_equal(out, data)
     assert zarr_io.crc32c(b"123456789") == 0xE3069283                           # the CRC-32C check value
+
+
+def test_mutated_frames_never_crash_the_decoder():
+    """Byte flips and truncations of valid frames: every call returns (0 or an error code), none takes the process down."""
+    lib = _cabi.lib()
+    rng = np.random.default_rng(0)
+    data = _camera_like(20000, np.uint16)
+    frames = [encode(data, c, 1, s, bs, sp) for c in (ZSTD, LZ4, ZLIB) if c in LIBS for s in (0, 1, 2)
+              for bs in (0, 2048) for sp in (0, 1)]
+    out = np.empty(data.nbytes + 64, np.uint8)
+    rejected = 0
+    for it in range(3000):
+        f = bytearray(frames[it % len(frames)])
+        for _ in range(int(rng.integers(1, 6))):
+            pos = int(rng.integers(0, min(len(f), 200) if rng.random() < 0.7 else len(f)))
+            f[pos] = int(rng.integers(0, 256))
+        if rng.random() < 0.2:
+            f = f[:int(rng.integers(16, len(f)))]
+        src = np.frombuffer(bytes(f), np.uint8)
+        nbytes = ctypes.c_int64()
+        rc = lib.shrimpy_blosc_info(src.ctypes.data, len(f), ctypes.byref(nbytes), None, None, None, None)
+        n = nbytes.value if rc == 0 and 0 <= nbytes.value <= out.nbytes else data.nbytes
+        rc = lib.shrimpy_blosc_decode(src.ctypes.data, len(f), out.ctypes.data, n, int(rng.integers(1, 5)))
+        assert rc in (_cabi.OK, _cabi.EINVAL, _cabi.ENOMEM)
+        rejected += rc != 0
+    assert rejected > 1000
