@@ -11,6 +11,14 @@
 
 namespace shrimpy {
 
+// A read-only 16-byte load the compiler may not reorder against its siblings or fold into one register set: a run of
+// these is issued back to back, which is the point (with plain __ldg the guarded loads were serialised through R8).
+__device__ __forceinline__ float4 ldg_in_order(const float4 *p) {
+    float4 r;
+    asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+}
+
 __global__ void minmax_init_kernel(unsigned *slots) {
     slots[0] = 0xffffffffu;
     slots[1] = 0u;
@@ -20,11 +28,19 @@ __global__ void __launch_bounds__(256) minmax_kernel(const float4 *__restrict__ 
                                                      long long n4, long long n, unsigned *slots) {
     float lo = FLT_MAX, hi = -FLT_MAX;
     const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
-        const float4 a = __ldg(v4 + i);
+    auto take = [&](const float4 a) {
         lo = fminf(fminf(lo, a.x), fminf(a.y, fminf(a.z, a.w)));
         hi = fmaxf(fmaxf(hi, a.x), fmaxf(a.y, fmaxf(a.z, a.w)));
+    };
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + 7 * stride < n4; i += 8 * stride) {          // eight 16-byte loads in flight per thread
+        float4 a[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) a[k] = ldg_in_order(v4 + i + k * stride);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) take(a[k]);
     }
+    for (; i < n4; i += stride) take(__ldg(v4 + i));
     for (long long i = 4 * n4 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         lo = fminf(lo, v[i]);
         hi = fmaxf(hi, v[i]);
@@ -47,31 +63,71 @@ __global__ void minmax_finish_kernel(const unsigned *slots, float *out) {
 
 // torch.histc: bin = floor((v - min) / (max - min) * nbins), v == max falls in the last bin, values outside ignored.
 // One sub-histogram per warp in shared memory keeps the atomics short.
+//
+// The bin is trunc((x - vmin) / range * 256) with an IEEE division (~10 instructions).  The fast path computes
+// k = trunc((x - vmin) * (2^23 / range)) instead: bin = k >> 15, and the low 15 bits are the position inside the bin.
+// The product is within 8e-5 of a bin width of the exact quotient (three float32 roundings of a value <= 256 plus the
+// truncation to 2^-15), so the two can disagree only when those bits are within 4 units of a bin edge; only such
+// voxels (flagged in a mask, ~2.4e-4 of uniform data) take the division, in a second, rarely executed block.
+// Bin 256 (x == vmax) has its own counter, folded into 255.
 __global__ void __launch_bounds__(256) hist256_kernel(const float *__restrict__ v, long long n, float vmin, float vmax,
                                                       unsigned long long *hist) {
-    __shared__ unsigned sub[8][256];
-    for (int i = threadIdx.x; i < 8 * 256; i += 256) (&sub[0][0])[i] = 0u;
+    constexpr int kTrash = 257;                       // counter for voxels the fast path does not bin
+    __shared__ unsigned sub[8][258];
+    for (int i = threadIdx.x; i < 8 * 258; i += 256) (&sub[0][0])[i] = 0u;
     __syncthreads();
     const float range = vmax - vmin;
+    const float scale = 8388608.0f / range;
     unsigned *mine = sub[threadIdx.x >> 5];
-    auto count = [&](float x) {
+    auto exact = [&](float x) {
         if (x >= vmin && x <= vmax) {
-            int b = (int)((x - vmin) / range * 256.0f);
-            b = min(b, 255);
-            atomicAdd(mine + b, 1u);
+            const int b = (int)((x - vmin) / range * 256.0f);
+            atomicAdd(mine + min(b, 255), 1u);
         }
+    };
+    // Branch-free: every voxel issues one shared atomic -- to its bin when it lies in range and clear of a bin edge,
+    // else to the trash counter.  Out-of-range values give k4 < 0 or k4 > 2^23 + 8 (or land on the first / last edge),
+    // NaN converts to 0 (an edge).  Returns true when the voxel has to be looked at by the exact path.
+    auto fast = [&](float x) -> bool {
+        const int k4 = (int)((x - vmin) * scale) + 4;
+        const bool interior = (k4 & 0x7ff8) != 0;
+        const bool ok = interior && (unsigned)k4 <= 8388608u + 8u;
+        atomicAdd(mine + (ok ? k4 >> 15 : kTrash), 1u);
+        return !interior;
+    };
+    auto count = [&](float x) {
+        if (fast(x)) exact(x);
     };
     const long long stride = (long long)gridDim.x * blockDim.x;
     const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    // 16-byte loads, two in flight per thread (the scalar loop was latency-bound at 2.2 TB/s); scalar head and tail
+    // 16-byte loads, four in flight per thread; scalar head and tail
     const long long head = min(n, (long long)((16u - (unsigned)(reinterpret_cast<uintptr_t>(v) & 15u)) & 15u) / 4);
     const long long n4 = (n - head) / 4;
     const float4 *v4 = reinterpret_cast<const float4 *>(v + head);
     long long i = tid;
-    for (; i + stride < n4; i += 2 * stride) {
-        const float4 a = __ldg(v4 + i), b = __ldg(v4 + i + stride);
-        count(a.x); count(a.y); count(a.z); count(a.w);
-        count(b.x); count(b.y); count(b.z); count(b.w);
+    if (i + 3 * stride < n4) {
+        // software pipeline: the four loads of the next batch are in flight while this batch is binned
+        float4 a = __ldg(v4 + i), b = __ldg(v4 + i + stride), c = __ldg(v4 + i + 2 * stride), d = __ldg(v4 + i + 3 * stride);
+        for (;;) {
+            const long long nx = i + 4 * stride;
+            const bool more = nx + 3 * stride < n4;
+            float4 na = a, nb = b, nc = c, nd = d;
+            if (more) {
+                na = __ldg(v4 + nx); nb = __ldg(v4 + nx + stride); nc = __ldg(v4 + nx + 2 * stride); nd = __ldg(v4 + nx + 3 * stride);
+            }
+            const float e[16] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w, d.x, d.y, d.z, d.w};
+            unsigned todo = 0;
+#pragma unroll
+            for (int q = 0; q < 16; ++q) todo |= (unsigned)fast(e[q]) << q;
+            if (todo) {
+#pragma unroll
+                for (int q = 0; q < 16; ++q)
+                    if ((todo >> q) & 1u) exact(e[q]);
+            }
+            i = nx;
+            if (!more) break;
+            a = na; b = nb; c = nc; d = nd;
+        }
     }
     for (; i < n4; i += stride) {
         const float4 a = __ldg(v4 + i);
@@ -83,12 +139,17 @@ __global__ void __launch_bounds__(256) hist256_kernel(const float *__restrict__ 
     for (int b = threadIdx.x; b < 256; b += 256) {
         unsigned long long t = 0;
 #pragma unroll
-        for (int w = 0; w < 8; ++w) t += sub[w][b];
+        for (int w = 0; w < 8; ++w) t += sub[w][b] + (b == 255 ? sub[w][256] : 0u);
         if (t) atomicAdd(hist + b, t);
     }
 }
 
-// sums[0..3] += (sum w, sum w*z, sum w*y, sum w*x); one (z, y) row per warp iteration, lanes along x
+// sums[0..3] += (sum w, sum w*z, sum w*y, sum w*x); one (z, y) row per warp iteration, lanes along x.
+// VEC: the row is read as a scalar head (up to the next 16-byte boundary), 16-byte vectors and a scalar tail -- rows of
+// a deskewed volume are 4 * 1279 bytes long, so the phase changes from row to row.  Twelve vectors per lane are in flight
+// -- a whole 1279-voxel row per warp -- (the scalar version, eight 4-byte loads per lane, stopped at 3.3 TB/s).  Sums are float32 within a row (per lane),
+// float64 across rows.
+template <bool VEC>
 __global__ void __launch_bounds__(256) com_kernel(const float *__restrict__ v, int Z, int Y, int X, float background,
                                                   double *sums) {
     double s = 0.0, sz = 0.0, sy = 0.0, sx = 0.0;
@@ -97,25 +158,46 @@ __global__ void __launch_bounds__(256) com_kernel(const float *__restrict__ v, i
     for (long long r = (long long)blockIdx.x * 8 + warp; r < rows; r += (long long)gridDim.x * 8) {
         const int z = (int)(r / Y), y = (int)(r - (long long)z * Y);
         const float *row = v + r * X;
-        float w_row = 0.f, wx_row = 0.f;   // float32 within one row (<= 32 * X/32 terms per lane), float64 across rows
-        // eight independent loads in flight per lane (the plain loop was latency-bound at 3.3 TB/s); the sums keep
-        // their sequential order, so the result does not change
-        int x = lane;
-        for (; x + 7 * 32 < X; x += 8 * 32) {
-            float v8[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v8[j] = __ldg(row + x + 32 * j);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const float w = fmaxf(v8[j] - background, 0.f);
-                w_row += w;
-                wx_row = fmaf(w, (float)(x + 32 * j), wx_row);
-            }
-        }
-        for (; x < X; x += 32) {
-            const float w = fmaxf(__ldg(row + x) - background, 0.f);
+        float w_row = 0.f, wx_row = 0.f;
+        auto take = [&](float val, float xf) {
+            const float w = fmaxf(val - background, 0.f);
             w_row += w;
-            wx_row = fmaf(w, (float)x, wx_row);
+            wx_row = fmaf(w, xf, wx_row);
+        };
+        if (VEC) {
+            const int head = min(X, (int)((4u - (unsigned)((r * X) & 3)) & 3u));   // v itself is 16-byte aligned
+            const int nvec = (X - head) >> 2;
+            const float4 *body = reinterpret_cast<const float4 *>(row + head);
+            auto take4 = [&](const float4 a, int j) {
+                const float x0 = (float)(head + 4 * j);
+                take(a.x, x0); take(a.y, x0 + 1.f); take(a.z, x0 + 2.f); take(a.w, x0 + 3.f);
+            };
+            // head and tail elements first (their loads overlap the vector loads), then chunks of kChunk vectors per
+            // lane, all issued before the first is consumed (slots past the row re-read its last vector and are skipped)
+            constexpr int kChunk = 12;
+            const int t = head + 4 * nvec + lane;
+            const float hv = lane < head ? __ldg(row + lane) : -INFINITY;
+            const float tv = t < X ? __ldg(row + t) : -INFINITY;
+            for (int j0 = lane; j0 < nvec + lane; j0 += 32 * kChunk) {
+                float4 a[kChunk];
+#pragma unroll
+                for (int k = 0; k < kChunk; ++k) a[k] = ldg_in_order(body + min(j0 + 32 * k, nvec - 1));
+#pragma unroll
+                for (int k = 0; k < kChunk; ++k)
+                    if (j0 + 32 * k < nvec) take4(a[k], j0 + 32 * k);
+            }
+            take(hv, (float)lane);
+            take(tv, (float)t);
+        } else {
+            int x = lane;
+            for (; x + 7 * 32 < X; x += 8 * 32) {
+                float v8[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v8[j] = __ldg(row + x + 32 * j);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) take(v8[j], (float)(x + 32 * j));
+            }
+            for (; x < X; x += 32) take(__ldg(row + x), (float)x);
         }
         s += (double)w_row;
         sx += (double)wx_row;
@@ -215,7 +297,11 @@ extern "C" int shrimpy_center_of_mass_device(const float *d_data, int Z, int Y, 
     if (!d_data || !d_sums4 || Z <= 0 || Y <= 0 || X <= 0) return fail(SHRIMPY_EINVAL, "center_of_mass: bad arguments");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     SHRIMPY_CUDA_TRY(cudaMemsetAsync(d_sums4, 0, 4 * sizeof(double), s));
-    com_kernel<<<grid_for((long long)Z * Y, 8 * 4), 256, 0, s>>>(d_data, Z, Y, X, background, d_sums4);
+    const int grid = grid_for((long long)Z * Y, 8 * 4);
+    if ((reinterpret_cast<uintptr_t>(d_data) & 15u) == 0 && X >= 64)
+        com_kernel<true><<<grid, 256, 0, s>>>(d_data, Z, Y, X, background, d_sums4);
+    else
+        com_kernel<false><<<grid, 256, 0, s>>>(d_data, Z, Y, X, background, d_sums4);
     count_launch();
     SHRIMPY_CUDA_TRY(cudaGetLastError());
     return SHRIMPY_OK;

@@ -118,3 +118,31 @@ def test_max_projection_equals_the_torch_expression(shape):
     assert torch.equal(red.max_projection(view, 100.0), (view - 100.0).clamp_min(0).amax(dim=0))
     with pytest.raises(ValueError):
         red.max_projection(vol[0])
+
+
+def test_histogram_bins_equal_the_ieee_division_form():
+    """The kernel bins with a multiply and falls back to the division only near a bin edge; the counts must equal
+    trunc((x - min) / (max - min) * 256) in float32 for every voxel -- including data that sits exactly on edges."""
+    import torch
+
+    from shrimpy_b200 import _cabi
+
+    rng = np.random.default_rng(5)
+    cases = {
+        "integers_on_edges": rng.integers(0, 513, 300001).astype(np.float32),            # range 512: every value on an edge
+        "uniform": rng.uniform(-3.0, 1000.0, 400003).astype(np.float32),
+        "thirds": (rng.integers(0, 769, 200000) / np.float32(3.0)).astype(np.float32),  # edges of a range that is not 2^k
+        "gamma": rng.gamma(2.0, 300.0, 500000).astype(np.float32),
+    }
+    for name, x in cases.items():
+        lo, hi = np.float32(x.min()), np.float32(x.max())
+        want = np.minimum(((x - lo) / (hi - lo) * np.float32(256.0)).astype(np.int64), 255)
+        want = np.bincount(want, minlength=256)
+        t = torch.from_numpy(x).cuda()
+        for view in (t, t[1:]):                                                          # aligned and unaligned start
+            hist = torch.empty(256, dtype=torch.int64, device="cuda")
+            _cabi.check(_cabi.lib().shrimpy_hist256_device(view.data_ptr(), view.numel(), float(lo), float(hi),
+                                                           hist.data_ptr(), torch.cuda.current_stream().cuda_stream))
+            ref = want if view is t else np.bincount(
+                np.minimum(((x[1:] - lo) / (hi - lo) * np.float32(256.0)).astype(np.int64), 255), minlength=256)
+            assert np.array_equal(hist.cpu().numpy(), ref), name

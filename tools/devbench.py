@@ -240,4 +240,18 @@ if __name__ == "__main__":
         r["deskew_plain_ms"] = t_ms(lambda: sb.deskew_zyx(raw, 30.0, 0.39, False, 3, out=out), reps=20)
         r["deskew_with_fused_range_ms"] = t_ms(lambda: sb.deskew_zyx(raw, 30.0, 0.39, False, 3, out=out, value_range=rng2), reps=20)
         r["percentile_given_range_ms"] = t_ms(lambda: red.percentile(out, 50.0, value_range=rng2))
+        # the kernels alone (C-ABI calls on preallocated buffers, no host round trip)
+        from shrimpy_b200 import _cabi
+        lib, st = _cabi.lib(), torch.cuda.current_stream().cuda_stream
+        hist = torch.empty(256, dtype=torch.int64, device="cuda")
+        sums = torch.empty(4, dtype=torch.float64, device="cuda")
+        mip = torch.empty((2048, 1279), dtype=torch.float32, device="cuda")
+        lo, hi = red.value_range(out)
+        r["hist_kernel_ms"] = t_ms(lambda: lib.shrimpy_hist256_device(out.data_ptr(), out.numel(), lo, hi, hist.data_ptr(), st), reps=20)
+        r["com_kernel_ms"] = t_ms(lambda: lib.shrimpy_center_of_mass_device(out.data_ptr(), 100, 2048, 1279, 100.0, sums.data_ptr(), st), reps=20)
+        r["zmax_kernel_ms"] = t_ms(lambda: lib.shrimpy_zmax_projection_device(out.data_ptr(), 100, 2048, 1279, 100.0, mip.data_ptr(), st), reps=20)
+        mm = torch.empty(2, dtype=torch.float32, device="cuda")
+        r["minmax_kernels_ms"] = t_ms(lambda: lib.shrimpy_minmax_device(out.data_ptr(), out.numel(), mm.data_ptr(), st), reps=20)
+        for k in ("hist", "com", "zmax"):
+            r[f"{k}_kernel_gbs"] = nbytes / r[f"{k}_kernel_ms"] / 1e6
         print(json.dumps({k: round(v, 3) for k, v in r.items()}), flush=True)
