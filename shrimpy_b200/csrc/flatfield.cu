@@ -8,13 +8,16 @@
 // can be fused into the deskew kernel (the deskew interpolates along z only, so scaling commutes with it).
 //
 // median_z_kernel: exact per-pixel median by byte-wise radix selection with shared-memory histograms.  A CTA owns
-// 64 consecutive pixels of one image row; per pass every thread walks its quarter of the scan axis (loads are
+// 64 consecutive pixels of one image row; per pass every thread walks its share of the scan axis (loads are
 // coalesced along x: the 64 pixels of a slice are 128 / 256 contiguous bytes) and counts one key byte of the keys
 // that still match the decided prefix into hist[byte][pixel] (the 32 lanes of a warp hit 32 different banks, so
-// the shared atomics never conflict).  Four threads per pixel then locate the bin holding the wanted rank.
-// uint16 needs 2 passes, float32 4; the slab of a CTA (Z x 64 pixels) is re-read from L1/L2, DRAM sees it once.
-// For even Z the upper middle value is the same key when it occurs often enough, else the smallest key above it
-// (one more min pass, only for CTAs that need it); the two are averaged (numpy.median / quantile(0.5) linear).
+// the shared atomics never conflict).  uint16 needs 2 passes, float32 4; the slab of a CTA (Z x 64 pixels) is re-read
+// from L1/L2, DRAM sees it once.  The bin holding the wanted rank is located by a two-level search on the packed
+// counters (warp g sums bins 32g..32g+31 of both pixels of a word at once; the group that holds the rank scans its
+// 32 bins).  For even Z the upper middle value is the same key when it occurs often enough, else the smallest key
+// above it: the next occupied bin of the last histogram, or -- when that lies in a higher prefix -- the minimum of
+// the keys above the prefix's range, which the last counting pass tracks in a register (two instructions per key; the
+// first version re-walked the column for it).  The two middle values are averaged (numpy.median / quantile(0.5)).
 // Z up to 65535 (the first version held a column in registers and stopped at Z = 1280).
 #include "common.cuh"
 
@@ -25,7 +28,6 @@ namespace shrimpy {
 
 constexpr int kMedThreads = 256;
 constexpr int kMedPixels = 64;                      // pixels per CTA
-constexpr int kMedQuarters = kMedThreads / kMedPixels;
 
 // order-preserving key: uint16 as is; float32 with the usual sign fix-up
 __device__ __forceinline__ uint32_t key_of(uint16_t v) { return v; }
@@ -51,12 +53,15 @@ template <typename T, bool PAIR>
 __global__ void __launch_bounds__(kMedThreads) median_z_kernel(const T *__restrict__ raw, float *__restrict__ pattern,
                                                                int Z, int Y, int X, long long sz, long long sy, int tiles_x) {
     constexpr int kWords = kMedPixels / 2;
+    constexpr int kGroups = kMedThreads / kWords;               // 8 warps, each owns 32 bins in the search
+    constexpr int kGroupBins = 256 / kGroups;
     extern __shared__ __align__(16) unsigned hist[];           // [256 bins][32 words], two 16-bit counters per word
-    __shared__ unsigned part[kMedQuarters][kMedPixels];         // counts per quarter of the bins
+    __shared__ unsigned part[kGroups][kWords];                  // packed counts of every group of 32 bins
     __shared__ unsigned s_prefix[kMedPixels];                   // decided high bytes of the wanted key
     __shared__ unsigned s_rank[kMedPixels];                     // rank still to be resolved among the matching keys
     __shared__ unsigned s_le[kMedPixels];                       // keys <= the selected key (after the last pass)
-    __shared__ unsigned s_above[kMedPixels];                    // smallest key above the selected one, + 1 (0 = not known yet)
+    __shared__ unsigned s_next[kMedPixels];                     // next occupied key of the last histogram + 1 (0 = none)
+    __shared__ unsigned s_far[kMedPixels];                      // min (key - limit) over keys above the last prefix's range
 
     constexpr int NB = sizeof(T);                               // key bytes: 2 or 4
     constexpr int PPT = PAIR ? 2 : 1;                           // pixels per thread while counting
@@ -64,34 +69,40 @@ __global__ void __launch_bounds__(kMedThreads) median_z_kernel(const T *__restri
     const int y = blockIdx.x / tiles_x;
     const int x0 = (blockIdx.x % tiles_x) * kMedPixels;
     const unsigned k_lo = (unsigned)(Z - 1) / 2, k_hi = (unsigned)Z / 2;   // the two middle ranks (equal for odd Z)
+    const bool even = k_hi != k_lo;
 
     // counting role: pixel(s) cpx (and cpx + 1), z slice cq
     const int cpx = PAIR ? 2 * (threadIdx.x % kWords) : threadIdx.x % kMedPixels;
     const int cq = PAIR ? threadIdx.x / kWords : threadIdx.x / kMedPixels;
-    const bool clive0 = x0 + cpx < X, clive1 = PAIR && x0 + cpx + 1 < X;
+    const bool clive0 = x0 + cpx < X, clive1 = PAIR && clive0;   // PAIR needs an even X, so pairs are never split by the edge
     const T *col = raw + (long long)y * sy + x0 + cpx;
-    // search role: pixel spx, quarter q of the bins
-    const int spx = threadIdx.x % kMedPixels, q = threadIdx.x / kMedPixels;
-    const int sword = spx >> 1, sshift = 16 * (spx & 1);
-    const bool slive = x0 + spx < X;
+    // search role: word w (pixels 2w, 2w + 1), bin group g (= the warp)
+    const int w = threadIdx.x % kWords, g = threadIdx.x / kWords;
 
-    for (int i = threadIdx.x; i < 256 * kWords; i += kMedThreads) hist[i] = 0;
-    if (q == 0) {
-        s_prefix[spx] = 0;
-        s_rank[spx] = k_lo;
-        s_le[spx] = 0;
-        s_above[spx] = 0;
+    for (int i = threadIdx.x; i < 256 * kWords / 4; i += kMedThreads) reinterpret_cast<uint4 *>(hist)[i] = make_uint4(0, 0, 0, 0);
+    if (threadIdx.x < kMedPixels) {
+        s_prefix[threadIdx.x] = 0;
+        s_rank[threadIdx.x] = k_lo;
+        s_le[threadIdx.x] = 0;
+        s_next[threadIdx.x] = 0;
+        s_far[threadIdx.x] = 0xffffffffu;
     }
     __syncthreads();
 
-#pragma unroll 1
+#pragma unroll
     for (int pass = 0; pass < NB; ++pass) {
+        constexpr int kLastPass = NB - 1;
         const int shift = 8 * (NB - 1 - pass);
+        const bool track = pass == kLastPass && even;          // also look for the smallest key above the prefix's range
         const unsigned prefix0 = s_prefix[cpx], prefix1 = PAIR ? s_prefix[cpx + 1] : 0u;
-        auto count = [&](T v, unsigned prefix, int px) {
+        const unsigned lim0 = (prefix0 + 1u) << 8, lim1 = (prefix1 + 1u) << 8;   // 0 = no key can lie above (wrapped)
+        unsigned far0 = 0xffffffffu, far1 = 0xffffffffu;
+        // keys below the limit wrap around to values larger than any true difference, so the minimum needs no test
+        auto count = [&](T v, unsigned prefix, unsigned lim, unsigned &far, int px) {
             const uint32_t key = key_of(v);
             if (pass == 0 || (key >> (shift + 8)) == prefix)
                 atomicAdd(&hist[((key >> shift) & 255u) * kWords + (px >> 1)], 1u << (16 * (px & 1)));
+            if (track) far = min(far, key - lim);
         };
         if (clive0) {
             // batches of independent loads keep enough bytes in flight (a plain loop was latency-bound)
@@ -103,98 +114,119 @@ __global__ void __launch_bounds__(kMedThreads) median_z_kernel(const T *__restri
 #pragma unroll
                     for (int i = 0; i < kBatch; ++i)
                         v[i] = __ldg(reinterpret_cast<const typename Pair<T>::type *>(col + (long long)(z + i * kSlices) * sz));
+                    if (clive1) {
 #pragma unroll
-                    for (int i = 0; i < kBatch; ++i) {
-                        count(v[i].x, prefix0, cpx);
-                        if (clive1) count(v[i].y, prefix1, cpx + 1);
+                        for (int i = 0; i < kBatch; ++i) {
+                            count(v[i].x, prefix0, lim0, far0, cpx);
+                            count(v[i].y, prefix1, lim1, far1, cpx + 1);
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < kBatch; ++i) count(v[i].x, prefix0, lim0, far0, cpx);
                     }
                 } else {
                     T v[kBatch];
 #pragma unroll
                     for (int i = 0; i < kBatch; ++i) v[i] = __ldg(col + (long long)(z + i * kSlices) * sz);
 #pragma unroll
-                    for (int i = 0; i < kBatch; ++i) count(v[i], prefix0, cpx);
+                    for (int i = 0; i < kBatch; ++i) count(v[i], prefix0, lim0, far0, cpx);
                 }
             }
             for (; z < Z; z += kSlices) {
-                count(__ldg(col + (long long)z * sz), prefix0, cpx);
-                if (clive1) count(__ldg(col + (long long)z * sz + 1), prefix1, cpx + 1);
+                count(__ldg(col + (long long)z * sz), prefix0, lim0, far0, cpx);
+                if (clive1) count(__ldg(col + (long long)z * sz + 1), prefix1, lim1, far1, cpx + 1);
+            }
+            if (track) {
+                if (lim0 != 0u) atomicMin(&s_far[cpx], far0);
+                if (clive1 && lim1 != 0u) atomicMin(&s_far[cpx + 1], far1);
             }
         }
         __syncthreads();
-        // four threads per pixel: counts of their 64 bins, then the quarter holding the rank scans again
+
+        // ---- search: which bin holds the rank?  Level 1: packed sums of the 32 bins of every group.
         unsigned mine = 0;
-        for (int b = 0; b < 64; ++b) mine += (hist[(q * 64 + b) * kWords + sword] >> sshift) & 0xffffu;
-        part[q][spx] = mine;
-        __syncthreads();
+#pragma unroll 8
+        for (int b = 0; b < kGroupBins; ++b) mine += hist[(g * kGroupBins + b) * kWords + w];   // halves cannot carry: <= Z
+        const unsigned rank0 = s_rank[2 * w], rank1 = s_rank[2 * w + 1];
+        const unsigned pre0 = s_prefix[2 * w], pre1 = s_prefix[2 * w + 1];
+        part[g][w] = mine;
+        __syncthreads();                       // part complete; everyone holds its copy of s_rank / s_prefix
         unsigned before = 0;
-        for (int i = 0; i < q; ++i) before += part[i][spx];
-        const unsigned rank = s_rank[spx], prefix = s_prefix[spx];
-        __syncthreads();                       // everyone has read s_rank / s_prefix before the owner rewrites them
-        if (rank >= before && rank < before + mine) {
-            unsigned acc = before;
-            int bin = q * 64;
-            for (;; ++bin) {
-                const unsigned c = (hist[bin * kWords + sword] >> sshift) & 0xffffu;
-                if (rank < acc + c) {
-                    s_prefix[spx] = (prefix << 8) | (unsigned)bin;
-                    s_rank[spx] = rank - acc;
-                    s_le[spx] += acc + (pass == NB - 1 ? c : 0u);   // keys below the bin (all passes) + the bin itself (last)
-                    break;
-                }
-                acc += c;
-            }
-            if (pass == NB - 1 && k_hi != k_lo) {
-                // the smallest key above the selected one is the next occupied bin of this pass, if there is one
-                for (int nb = bin + 1; nb < 256; ++nb)
-                    if ((hist[nb * kWords + sword] >> sshift) & 0xffffu) {
-                        s_above[spx] = ((prefix << 8) | (unsigned)nb) + 1u;
-                        break;
+        for (int i = 0; i < g; ++i) before += part[i][w];
+        const unsigned b0 = before & 0xffffu, b1 = before >> 16, m0 = mine & 0xffffu, m1 = mine >> 16;
+        const bool own0 = rank0 >= b0 && rank0 < b0 + m0, own1 = rank1 >= b1 && rank1 < b1 + m1;
+        if (own0 || own1) {
+            // Level 2: the group that holds a pixel's rank scans its 32 bins (both pixels of the word in one walk)
+            unsigned acc0 = b0, acc1 = b1;
+            bool open0 = own0, open1 = own1;
+            int bin0 = 0, bin1 = 0;
+            for (int bin = g * kGroupBins; open0 || open1; ++bin) {
+                const unsigned word = hist[bin * kWords + w];
+                const unsigned c0 = word & 0xffffu, c1 = word >> 16;
+                if (open0) {
+                    if (rank0 < acc0 + c0) {
+                        open0 = false;
+                        bin0 = bin;
+                        s_prefix[2 * w] = (pre0 << 8) | (unsigned)bin;
+                        s_rank[2 * w] = rank0 - acc0;
+                        s_le[2 * w] += acc0 + (pass == kLastPass ? c0 : 0u);   // keys below the bin (all passes) + the bin (last)
+                    } else {
+                        acc0 += c0;
                     }
+                }
+                if (open1) {
+                    if (rank1 < acc1 + c1) {
+                        open1 = false;
+                        bin1 = bin;
+                        s_prefix[2 * w + 1] = (pre1 << 8) | (unsigned)bin;
+                        s_rank[2 * w + 1] = rank1 - acc1;
+                        s_le[2 * w + 1] += acc1 + (pass == kLastPass ? c1 : 0u);
+                    } else {
+                        acc1 += c1;
+                    }
+                }
+            }
+            if (track) {
+                // the smallest key above the selected one inside this prefix: the next occupied bin, skipping empty groups
+                auto next_bin = [&](int bin, int half) -> int {
+                    const int sh = 16 * half;
+                    for (int nb = bin + 1; nb < 256; ++nb) {
+                        if ((nb % kGroupBins) == 0 && ((part[nb / kGroupBins][w] >> sh) & 0xffffu) == 0u) {
+                            nb += kGroupBins - 1;
+                            continue;
+                        }
+                        if ((hist[nb * kWords + w] >> sh) & 0xffffu) return nb;
+                    }
+                    return -1;
+                };
+                if (own0 && s_le[2 * w] <= k_hi) {
+                    const int nb = next_bin(bin0, 0);
+                    if (nb >= 0) s_next[2 * w] = ((pre0 << 8) | (unsigned)nb) + 1u;
+                }
+                if (own1 && s_le[2 * w + 1] <= k_hi) {
+                    const int nb = next_bin(bin1, 1);
+                    if (nb >= 0) s_next[2 * w + 1] = ((pre1 << 8) | (unsigned)nb) + 1u;
+                }
             }
         }
         __syncthreads();
         if (pass + 1 < NB) {
-            for (int i = threadIdx.x; i < 256 * kWords; i += kMedThreads) hist[i] = 0;
+            for (int i = threadIdx.x; i < 256 * kWords / 4; i += kMedThreads)
+                reinterpret_cast<uint4 *>(hist)[i] = make_uint4(0, 0, 0, 0);
             __syncthreads();
         }
     }
 
-    if (k_hi != k_lo) {
-        // upper middle value: the same key if enough keys are <= it, else the smallest key above it; that one is
-        // known from the last histogram unless it differs in a higher byte -- then one min pass over the column
-        const bool need0 = clive0 && s_le[cpx] <= k_hi && s_above[cpx] == 0;
-        const bool need1 = clive1 && s_le[cpx + 1] <= k_hi && s_above[cpx + 1] == 0;
-        if (__syncthreads_or(need0 || need1)) {
-            if (q == 0 && s_above[spx] == 0) s_above[spx] = 0xffffffffu;
-            __syncthreads();
-            if (need0 || need1) {
-                const uint32_t m0 = s_prefix[cpx], m1 = PAIR ? s_prefix[cpx + 1] : 0u;
-                uint32_t best0 = 0xffffffffu, best1 = 0xffffffffu;
-                for (int z = cq; z < Z; z += kSlices) {
-                    if (need0) {
-                        const uint32_t key = key_of(__ldg(col + (long long)z * sz));
-                        if (key > m0) best0 = min(best0, key);
-                    }
-                    if (need1) {
-                        const uint32_t key = key_of(__ldg(col + (long long)z * sz + 1));
-                        if (key > m1) best1 = min(best1, key);
-                    }
-                }
-                // stored + 1 like the histogram result
-                if (need0 && best0 != 0xffffffffu) atomicMin(&s_above[cpx], best0 + 1u);
-                if (need1 && best1 != 0xffffffffu) atomicMin(&s_above[cpx + 1], best1 + 1u);
-            }
-            __syncthreads();
-        }
-    }
-    if (q == 0 && slive) {
-        const uint32_t m_lo = s_prefix[spx];
-        const uint32_t m_hi = (k_hi == k_lo || s_le[spx] > k_hi) ? m_lo : s_above[spx] - 1u;
+    if (threadIdx.x < kMedPixels && x0 + (int)threadIdx.x < X) {
+        const int px = threadIdx.x;
+        const uint32_t m_lo = s_prefix[px];
+        uint32_t m_hi = m_lo;                                   // odd Z, or enough keys <= m_lo
+        if (even && s_le[px] <= k_hi)
+            m_hi = s_next[px] ? s_next[px] - 1u : s_far[px] + (((m_lo >> 8) + 1u) << 8);
         // numpy: mean of the two middle values (float32 data stays float32)
         const float lo = value_of<T>(m_lo), hi = value_of<T>(m_hi);
-        const float med = (k_hi == k_lo) ? lo : (sizeof(T) == 2) ? 0.5f * (lo + hi) : __fmul_rn(__fadd_rn(lo, hi), 0.5f);
-        pattern[(long long)y * X + x0 + spx] = med;
+        const float med = !even ? lo : (sizeof(T) == 2) ? 0.5f * (lo + hi) : __fmul_rn(__fadd_rn(lo, hi), 0.5f);
+        pattern[(long long)y * X + x0 + px] = med;
     }
 }
 
