@@ -41,6 +41,21 @@ template <> __device__ __forceinline__ float value_of<float>(uint32_t k) {
     return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
 }
 
+// Shared-memory reductions by address, unconditional and predicated.  Written in PTX because the C++ form
+// `if (match) atomicAdd(...)` compiles to a branch per key that re-derives the shared window base inside it
+// (9 instructions, 71 M warp instructions per launch); this is one predicated ATOMS.
+__device__ __forceinline__ void red_shared(unsigned addr, unsigned val) {
+    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(val) : "memory");
+}
+__device__ __forceinline__ void red_shared_if(bool on, unsigned addr, unsigned val) {
+    asm volatile(
+        "{\n"
+        " .reg .pred q;\n"
+        " setp.ne.u32 q, %0, 0;\n"
+        " @q red.shared.add.u32 [%1], %2;\n"
+        "}" ::"r"((unsigned)on), "r"(addr), "r"(val) : "memory");
+}
+
 template <typename T> struct Pair;
 template <> struct Pair<uint16_t> { typedef ushort2 type; };
 template <> struct Pair<float> { typedef float2 type; };
@@ -93,16 +108,20 @@ __global__ void __launch_bounds__(kMedThreads) median_z_kernel(const T *__restri
     for (int pass = 0; pass < NB; ++pass) {
         constexpr int kLastPass = NB - 1;
         const int shift = 8 * (NB - 1 - pass);
-        const bool track = pass == kLastPass && even;          // also look for the smallest key above the prefix's range
+        const bool last = pass == kLastPass;                   // the last pass also tracks the smallest key above the prefix's range
+        const bool track = last && even;
         const unsigned prefix0 = s_prefix[cpx], prefix1 = PAIR ? s_prefix[cpx + 1] : 0u;
         const unsigned lim0 = (prefix0 + 1u) << 8, lim1 = (prefix1 + 1u) << 8;   // 0 = no key can lie above (wrapped)
         unsigned far0 = 0xffffffffu, far1 = 0xffffffffu;
         // keys below the limit wrap around to values larger than any true difference, so the minimum needs no test
+        const unsigned hbase = smem_u32(hist) + (unsigned)(cpx >> 1) * 4u;      // this thread's word of every bin row
         auto count = [&](T v, unsigned prefix, unsigned lim, unsigned &far, int px) {
             const uint32_t key = key_of(v);
-            if (pass == 0 || (key >> (shift + 8)) == prefix)
-                atomicAdd(&hist[((key >> shift) & 255u) * kWords + (px >> 1)], 1u << (16 * (px & 1)));
-            if (track) far = min(far, key - lim);
+            const unsigned addr = hbase + ((key >> shift) & 255u) * (unsigned)(kWords * 4);
+            const unsigned one = 1u << (16 * (px & 1));
+            if (pass == 0) red_shared(addr, one);
+            else red_shared_if((key >> (shift + 8)) == prefix, addr, one);
+            if (last) far = min(far, key - lim);          // (unconditionally: a test on `even` per key costs as much)
         };
         if (clive0) {
             // batches of independent loads keep enough bytes in flight (a plain loop was latency-bound)
@@ -156,35 +175,34 @@ __global__ void __launch_bounds__(kMedThreads) median_z_kernel(const T *__restri
         const unsigned b0 = before & 0xffffu, b1 = before >> 16, m0 = mine & 0xffffu, m1 = mine >> 16;
         const bool own0 = rank0 >= b0 && rank0 < b0 + m0, own1 = rank1 >= b1 && rank1 < b1 + m1;
         if (own0 || own1) {
-            // Level 2: the group that holds a pixel's rank scans its 32 bins (both pixels of the word in one walk)
-            unsigned acc0 = b0, acc1 = b1;
-            bool open0 = own0, open1 = own1;
+            // Level 2: the group that holds a pixel's rank scans its 32 bins, one pixel of the word after the other
+            // (a joint walk with per-pixel flags cost 45 instructions per bin)
             int bin0 = 0, bin1 = 0;
-            for (int bin = g * kGroupBins; open0 || open1; ++bin) {
-                const unsigned word = hist[bin * kWords + w];
-                const unsigned c0 = word & 0xffffu, c1 = word >> 16;
-                if (open0) {
-                    if (rank0 < acc0 + c0) {
-                        open0 = false;
-                        bin0 = bin;
-                        s_prefix[2 * w] = (pre0 << 8) | (unsigned)bin;
-                        s_rank[2 * w] = rank0 - acc0;
-                        s_le[2 * w] += acc0 + (pass == kLastPass ? c0 : 0u);   // keys below the bin (all passes) + the bin (last)
-                    } else {
-                        acc0 += c0;
-                    }
+            if (own0) {
+                unsigned acc = b0, c;
+                int bin = g * kGroupBins;
+                for (;; ++bin) {
+                    c = hist[bin * kWords + w] & 0xffffu;
+                    if (rank0 < acc + c) break;
+                    acc += c;
                 }
-                if (open1) {
-                    if (rank1 < acc1 + c1) {
-                        open1 = false;
-                        bin1 = bin;
-                        s_prefix[2 * w + 1] = (pre1 << 8) | (unsigned)bin;
-                        s_rank[2 * w + 1] = rank1 - acc1;
-                        s_le[2 * w + 1] += acc1 + (pass == kLastPass ? c1 : 0u);
-                    } else {
-                        acc1 += c1;
-                    }
+                bin0 = bin;
+                s_prefix[2 * w] = (pre0 << 8) | (unsigned)bin;
+                s_rank[2 * w] = rank0 - acc;
+                s_le[2 * w] += acc + (pass == kLastPass ? c : 0u);   // keys below the bin (all passes) + the bin (last)
+            }
+            if (own1) {
+                unsigned acc = b1, c;
+                int bin = g * kGroupBins;
+                for (;; ++bin) {
+                    c = hist[bin * kWords + w] >> 16;
+                    if (rank1 < acc + c) break;
+                    acc += c;
                 }
+                bin1 = bin;
+                s_prefix[2 * w + 1] = (pre1 << 8) | (unsigned)bin;
+                s_rank[2 * w + 1] = rank1 - acc;
+                s_le[2 * w + 1] += acc + (pass == kLastPass ? c : 0u);
             }
             if (track) {
                 // the smallest key above the selected one inside this prefix: the next occupied bin, skipping empty groups
