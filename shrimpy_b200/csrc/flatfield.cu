@@ -23,6 +23,7 @@
 
 #include <algorithm>
 #include <cfloat>
+#include <cstring>
 
 namespace shrimpy {
 
@@ -133,15 +134,32 @@ __global__ void __launch_bounds__(kMedThreads) median_z_kernel(const T *__restri
 #pragma unroll
                     for (int i = 0; i < kBatch; ++i)
                         v[i] = __ldg(reinterpret_cast<const typename Pair<T>::type *>(col + (long long)(z + i * kSlices) * sz));
-                    if (clive1) {
+                    if constexpr (sizeof(T) == 2) {
+                        // uint16 pairs stay one 32-bit word: key bytes come out with one PRMT each, both prefixes are
+                        // compared through one XOR (the generic path spends 7.5 / 11 instructions per key on this)
+                        const unsigned both = (prefix0 << 8) | (prefix1 << 24);
+#pragma unroll
+                        for (int i = 0; i < kBatch; ++i) {
+                            unsigned word;
+                            memcpy(&word, &v[i], 4);
+                            if (pass == 0) {
+                                red_shared(hbase + __byte_perm(word, 0, 0x4441) * (unsigned)(kWords * 4), 1u);
+                                red_shared(hbase + __byte_perm(word, 0, 0x4443) * (unsigned)(kWords * 4), 0x10000u);
+                            } else {
+                                const unsigned diff = word ^ both;
+                                red_shared_if((diff & 0x0000ff00u) == 0u, hbase + (word & 0xffu) * (unsigned)(kWords * 4), 1u);
+                                red_shared_if((diff & 0xff000000u) == 0u,
+                                              hbase + __byte_perm(word, 0, 0x4442) * (unsigned)(kWords * 4), 0x10000u);
+                                far0 = min(far0, (word & 0xffffu) - lim0);
+                                far1 = min(far1, (word >> 16) - lim1);
+                            }
+                        }
+                    } else {
 #pragma unroll
                         for (int i = 0; i < kBatch; ++i) {
                             count(v[i].x, prefix0, lim0, far0, cpx);
                             count(v[i].y, prefix1, lim1, far1, cpx + 1);
                         }
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < kBatch; ++i) count(v[i].x, prefix0, lim0, far0, cpx);
                     }
                 } else {
                     T v[kBatch];
