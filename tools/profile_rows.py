@@ -1,6 +1,6 @@
 """One launch of every kernel of the rows either side of the deskew (flat-field, tracking reductions), for ncu.
 
-    ncu --set full --clock-control none -k regex:"median_z|pattern_|apply_scale|minmax_kernel|hist256|com_kernel|deskew_tma" \
+    ncu --set full --clock-control none -k regex:"median_z|pattern_|apply_scale|minmax_kernel|hist256|com_kernel|zmax|deskew_tma" \
         -o gpurun_out/prof_rows python tools/profile_rows.py
 """
 import sys
@@ -24,5 +24,6 @@ del ff32
 vmin, vmax = red.value_range(out)                                   # minmax
 bg = red.percentile(out, 50.0)                                      # minmax + hist256
 com = red.intensity_center_of_mass(out, bg)                         # com
+mip = red.max_projection(out, bg)                                   # zmax
 torch.cuda.synchronize()
 print("range", vmin, vmax, "background", bg, "centre of mass", com)
