@@ -250,6 +250,12 @@ if __name__ == "__main__":
         r["hist_kernel_ms"] = t_ms(lambda: lib.shrimpy_hist256_device(out.data_ptr(), out.numel(), lo, hi, hist.data_ptr(), st), reps=20)
         r["com_kernel_ms"] = t_ms(lambda: lib.shrimpy_center_of_mass_device(out.data_ptr(), 100, 2048, 1279, 100.0, sums.data_ptr(), st), reps=20)
         r["zmax_kernel_ms"] = t_ms(lambda: lib.shrimpy_zmax_projection_device(out.data_ptr(), 100, 2048, 1279, 100.0, mip.data_ptr(), st), reps=20)
+        # a volume whose voxels crowd into a few bins (background-dominated images): same-address shared atomics
+        flat = torch.randn((100, 2048, 1279), device="cuda") * 2.0 + 500.0
+        r["hist_kernel_crowded_ms"] = t_ms(lambda: lib.shrimpy_hist256_device(flat.data_ptr(), flat.numel(), 0.0, 1000.0, hist.data_ptr(), st), reps=10)
+        flat.fill_(500.0)
+        r["hist_kernel_constant_ms"] = t_ms(lambda: lib.shrimpy_hist256_device(flat.data_ptr(), flat.numel(), 0.0, 1000.0, hist.data_ptr(), st), reps=10)
+        del flat
         mm = torch.empty(2, dtype=torch.float32, device="cuda")
         r["minmax_kernels_ms"] = t_ms(lambda: lib.shrimpy_minmax_device(out.data_ptr(), out.numel(), mm.data_ptr(), st), reps=20)
         for k in ("hist", "com", "zmax"):
