@@ -194,56 +194,44 @@ __global__ void __launch_bounds__(kMedThreads) median_z_kernel(const T *__restri
         const bool own0 = rank0 >= b0 && rank0 < b0 + m0, own1 = rank1 >= b1 && rank1 < b1 + m1;
         if (own0 || own1) {
             // Level 2: the group that holds a pixel's rank scans its 32 bins, one pixel of the word after the other
-            // (a joint walk with per-pixel flags cost 45 instructions per bin)
-            int bin0 = 0, bin1 = 0;
-            if (own0) {
-                unsigned acc = b0, c;
-                int bin = g * kGroupBins;
-                for (;; ++bin) {
-                    c = hist[bin * kWords + w] & 0xffffu;
-                    if (rank0 < acc + c) break;
+            // (a joint walk with per-pixel flags cost 45 instructions per bin).  The walks run on a stepped pointer to the
+            // pixel's 16-bit counter: load, add, compare, branch.
+            constexpr int kStep = 2 * kWords;                                  // counters (uint16) from one bin to the next
+            const unsigned short *counters = reinterpret_cast<const unsigned short *>(hist) + 2 * w;
+            auto select = [&](int half, unsigned rank, unsigned before, unsigned pre) -> int {
+                const unsigned short *p = counters + half + g * kGroupBins * kStep;
+                unsigned acc = before, c = *p;
+                while (rank >= acc + c) {
                     acc += c;
+                    p += kStep;
+                    c = *p;
                 }
-                bin0 = bin;
-                s_prefix[2 * w] = (pre0 << 8) | (unsigned)bin;
-                s_rank[2 * w] = rank0 - acc;
-                s_le[2 * w] += acc + (pass == kLastPass ? c : 0u);   // keys below the bin (all passes) + the bin (last)
-            }
-            if (own1) {
-                unsigned acc = b1, c;
-                int bin = g * kGroupBins;
-                for (;; ++bin) {
-                    c = hist[bin * kWords + w] >> 16;
-                    if (rank1 < acc + c) break;
-                    acc += c;
-                }
-                bin1 = bin;
-                s_prefix[2 * w + 1] = (pre1 << 8) | (unsigned)bin;
-                s_rank[2 * w + 1] = rank1 - acc;
-                s_le[2 * w + 1] += acc + (pass == kLastPass ? c : 0u);
-            }
-            if (track) {
-                // the smallest key above the selected one inside this prefix: the next occupied bin, skipping empty groups
-                auto next_bin = [&](int bin, int half) -> int {
-                    const int sh = 16 * half;
-                    for (int nb = bin + 1; nb < 256; ++nb) {
-                        if ((nb % kGroupBins) == 0 && ((part[nb / kGroupBins][w] >> sh) & 0xffffu) == 0u) {
-                            nb += kGroupBins - 1;
-                            continue;
-                        }
-                        if ((hist[nb * kWords + w] >> sh) & 0xffffu) return nb;
+                const int bin = (int)((p - counters) / kStep);
+                const int px = 2 * w + half;
+                s_prefix[px] = (pre << 8) | (unsigned)bin;
+                s_rank[px] = rank - acc;
+                const unsigned le = s_le[px] + acc + (last ? c : 0u);         // keys below the bin (all passes) + the bin (last)
+                s_le[px] = le;
+                if (track && le <= k_hi) {
+                    // the smallest key above the selected one inside this prefix: the next occupied bin -- the rest of
+                    // this group, then the first later group whose packed count is not zero
+                    int nb = -1;
+                    const unsigned short *q = p + kStep;
+                    for (int b = bin + 1; b < (g + 1) * kGroupBins; ++b, q += kStep)
+                        if (*q) { nb = b; break; }
+                    for (int gg = g + 1; nb < 0 && gg < kGroups; ++gg) {
+                        if (((part[gg][w] >> (16 * half)) & 0xffffu) == 0u) continue;
+                        q = counters + half + gg * kGroupBins * kStep;
+                        int b = gg * kGroupBins;
+                        while (*q == 0) { q += kStep; ++b; }
+                        nb = b;
                     }
-                    return -1;
-                };
-                if (own0 && s_le[2 * w] <= k_hi) {
-                    const int nb = next_bin(bin0, 0);
-                    if (nb >= 0) s_next[2 * w] = ((pre0 << 8) | (unsigned)nb) + 1u;
+                    if (nb >= 0) s_next[px] = ((pre << 8) | (unsigned)nb) + 1u;
                 }
-                if (own1 && s_le[2 * w + 1] <= k_hi) {
-                    const int nb = next_bin(bin1, 1);
-                    if (nb >= 0) s_next[2 * w + 1] = ((pre1 << 8) | (unsigned)nb) + 1u;
-                }
-            }
+                return bin;
+            };
+            if (own0) select(0, rank0, b0, pre0);
+            if (own1) select(1, rank1, b1, pre1);
         }
         __syncthreads();
         if (pass + 1 < NB) {
