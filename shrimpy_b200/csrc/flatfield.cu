@@ -138,6 +138,9 @@ __global__ void __launch_bounds__(kMedThreads) median_z_kernel(const T *__restri
                         // uint16 pairs stay one 32-bit word: key bytes come out with one PRMT each, both prefixes are
                         // compared through one XOR (the generic path spends 7.5 / 11 instructions per key on this)
                         const unsigned both = (prefix0 << 8) | (prefix1 << 24);
+                        // the same wrap-around minimum as `count`, on 16-bit halves with one DPX instruction per pair
+                        const unsigned neglims = ((0u - lim0) & 0xffffu) | ((0u - lim1) << 16);
+                        unsigned far2 = 0xffffffffu;
 #pragma unroll
                         for (int i = 0; i < kBatch; ++i) {
                             unsigned word;
@@ -150,10 +153,11 @@ __global__ void __launch_bounds__(kMedThreads) median_z_kernel(const T *__restri
                                 red_shared_if((diff & 0x0000ff00u) == 0u, hbase + (word & 0xffu) * (unsigned)(kWords * 4), 1u);
                                 red_shared_if((diff & 0xff000000u) == 0u,
                                               hbase + __byte_perm(word, 0, 0x4442) * (unsigned)(kWords * 4), 0x10000u);
-                                far0 = min(far0, (word & 0xffffu) - lim0);
-                                far1 = min(far1, (word >> 16) - lim1);
+                                far2 = __viaddmin_u16x2(word, neglims, far2);   // both halves: min(key - lim, far) mod 2^16
                             }
                         }
+                        far0 = min(far0, far2 & 0xffffu);
+                        far1 = min(far1, far2 >> 16);
                     } else {
 #pragma unroll
                         for (int i = 0; i < kBatch; ++i) {

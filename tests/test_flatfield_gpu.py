@@ -56,6 +56,27 @@ def test_median_pattern_is_exact(env, shape, dtype):
     assert np.array_equal(got, ffo.flat_field_pattern(vol))
 
 
+@pytest.mark.parametrize("shape", [(128, 3, 64), (600, 2, 128), (130, 2, 66), (64, 2, 31)])
+def test_median_full_range_even_z(env, shape):
+    """Keys spread over the whole uint16 range with an even Z: the two middle values usually sit in different high
+    bytes, so the upper one comes from the minimum the last counting pass tracks (packed 16-bit DPX form in the paired
+    path, 32-bit form in the scalar one); columns at the extremes (0, 65535) exercise the wrap-around limits."""
+    torch, ff, ffo, _ = env
+    rng = np.random.default_rng(sum(shape))
+    vol = rng.integers(0, 65536, shape, dtype=np.uint16)
+    vol[:, 0, 1] = 65535
+    vol[: shape[0] // 2, 0, 2] = 65535                       # lower middle 65535 is impossible, upper middle is
+    vol[shape[0] // 2:, 0, 2] = 0
+    vol[: shape[0] // 2, 0, 3] = 65280                       # 0xff00 / 0xffff: both in the last high byte
+    vol[shape[0] // 2:, 0, 3] = 65535
+    vol[:, 0, 4] = np.where(np.arange(shape[0]) % 2 == 0, 255, 256).astype(np.uint16)   # neighbours across a high byte
+    got = ff.flat_field_pattern(torch.from_numpy(vol).cuda()).cpu().numpy()
+    assert np.array_equal(got, ffo.flat_field_pattern(vol))
+    f32 = (vol.astype(np.float32) - 32768.0) * np.float32(1.7)
+    got = ff.flat_field_pattern(torch.from_numpy(f32).cuda()).cpu().numpy()
+    assert np.array_equal(got, ffo.flat_field_pattern(f32))
+
+
 def test_scale_and_standalone_correction(env):
     torch, ff, ffo, _ = env
     vol = _bright_field((40, 12, 96), seed=5)
