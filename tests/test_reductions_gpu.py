@@ -133,6 +133,7 @@ def test_histogram_bins_equal_the_ieee_division_form():
         "uniform": rng.uniform(-3.0, 1000.0, 400003).astype(np.float32),
         "thirds": (rng.integers(0, 769, 200000) / np.float32(3.0)).astype(np.float32),  # edges of a range that is not 2^k
         "gamma": rng.gamma(2.0, 300.0, 500000).astype(np.float32),
+        "large": rng.normal(300.0, 40.0, 12_000_001).astype(np.float32),                 # several pipelined batches per thread
     }
     for name, x in cases.items():
         lo, hi = np.float32(x.min()), np.float32(x.max())
@@ -146,3 +147,25 @@ def test_histogram_bins_equal_the_ieee_division_form():
             ref = want if view is t else np.bincount(
                 np.minimum(((x[1:] - lo) / (hi - lo) * np.float32(256.0)).astype(np.int64), 255), minlength=256)
             assert np.array_equal(hist.cpu().numpy(), ref), name
+
+
+@pytest.mark.parametrize("shape", [(5, 7, 1279), (3, 4, 2101), (2, 3, 64), (4, 5, 67)])
+def test_center_of_mass_vector_path_against_float64(shape):
+    """Rows whose 16-byte phase changes from row to row (X % 4 != 0), rows longer than one chunk of vectors (X > 1536),
+    the shortest vectorised row (X = 64), and an unaligned base pointer (scalar kernel): all against a float64 sum."""
+    import torch
+
+    from shrimpy_b200 import reductions as red
+
+    vol = _volume(21, shape)
+    for bg in (0.0, 350.0):
+        w = np.clip(vol.astype(np.float64) - bg, 0, None)
+        want = [(w.sum(axis=tuple(a for a in range(3) if a != ax)) * np.arange(shape[ax])).sum() / w.sum() for ax in range(3)]
+        t = torch.from_numpy(vol).cuda()
+        got = red.intensity_center_of_mass(t, background=bg).cpu().numpy()
+        assert np.allclose(got, want, rtol=2e-6, atol=1e-4), (shape, bg, got, want)
+        flat = torch.empty(vol.size + 1, dtype=torch.float32, device="cuda")
+        view = flat[1:].view(shape)                                   # 4-byte aligned only
+        view.copy_(t)
+        got = red.intensity_center_of_mass(view, background=bg).cpu().numpy()
+        assert np.allclose(got, want, rtol=2e-6, atol=1e-4), (shape, bg, "unaligned")
