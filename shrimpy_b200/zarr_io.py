@@ -345,7 +345,12 @@ class ZarrArray:
         if len(blob) < index_bytes:
             raise IOError(f"{path}: {len(blob)} bytes cannot hold a shard index of {index_bytes}")
         raw_index = blob[len(blob) - index_bytes:] if self.shard_index_at_end else blob[:index_bytes]
-        table = np.frombuffer(raw_index[:n_inner * 16].tobytes(), dtype="<u8").reshape(n_inner, 2)
+        index_payload = raw_index[:n_inner * 16].tobytes()
+        if self.shard_index_crc:
+            stored = int.from_bytes(raw_index[n_inner * 16:n_inner * 16 + 4].tobytes(), "little")
+            if crc32c(index_payload) != stored:
+                raise IOError(f"{path}: shard index checksum mismatch (crc32c)")
+        table = np.frombuffer(index_payload, dtype="<u8").reshape(n_inner, 2)
         jobs = []
         for flat, (offset, nbytes) in enumerate(table):
             sub = np.unravel_index(flat, per_axis)
@@ -431,42 +436,52 @@ class ZarrArray:
         ``piece_bytes`` for uncompressed chunks (``os.preadv`` straight into the destination, the GIL is
         released), whole (inner) chunks for compressed ones, decoded in place (the native decoders release the
         GIL too) -- and run concurrently.  Only the part of a partial last chunk that holds data is read.
+        Chunks (or shards) that also tile Y and X are decoded through a scratch block and copied into their window
+        of ``out`` -- any regular chunking of a TCZYX array can be read, the z-slab layouts are the fast ones.
         """
         self._check_tczyx()
         Z, Y, X = self.shape[2:]
         if tuple(out.shape) != (Z, Y, X) or out.dtype != self.dtype or not out.flags.c_contiguous:
             raise ValueError(f"out must be a C-contiguous {self.dtype} array of shape {(Z, Y, X)}")
-        zc = self.chunks[2]
+        if self.chunks[0] != 1 or self.chunks[1] != 1:
+            raise NotImplementedError(f"stack streaming needs chunks of one timepoint and channel, got {self.chunks}")
+        zc, yc, xc = self.chunks[2:]
+        slabs = (yc, xc) == (Y, X)                          # every chunk is a contiguous z-slab of the stack
+        cells = [(kz, ky, kx) for kz in range(-(-Z // zc)) for ky in range(-(-Y // yc)) for kx in range(-(-X // xc))]
         tasks, listed = [], 0
-        pieces = self.stack_chunks(t, c)
         workers = getattr(pool, "_max_workers", 1) if pool is not None else 1
-        for index, zs in pieces:
-            nz = zs.stop - zs.start
+        for kz, ky, kx in cells:
+            index = (t, c, kz, ky, kx)
+            window = out[kz * zc:(kz + 1) * zc, ky * yc:(ky + 1) * yc, kx * xc:(kx + 1) * xc]   # clipped at the edges
+            nz = window.shape[0]
             path = self.chunk_path(index)
             if not path.exists():
-                out[zs] = self.fill_value
+                window[...] = self.fill_value
             elif self.shard_inner is not None:
-                inner_count = int(np.prod([c // i for c, i in zip(self.chunks, self.shard_inner)]))
-                threads = max(1, workers // max(1, inner_count * len(pieces)))
-                jobs, nbytes = self._shard_jobs(path, out[zs][None, None], threads)
+                inner_count = int(np.prod([n // i for n, i in zip(self.chunks, self.shard_inner)]))
+                threads = max(1, workers // max(1, inner_count * len(cells)))
+                jobs, nbytes = self._shard_jobs(path, window[None, None], threads)
                 tasks += jobs
                 listed += nbytes
+            elif not slabs:
+                tasks.append((self._read_window, (index, window)))
             elif not self.compressed:
-                view = memoryview(out[zs].reshape(-1).view(np.uint8))       # the data-bearing prefix of the chunk
+                view = memoryview(window.reshape(-1).view(np.uint8))          # the data-bearing prefix of the chunk
                 for off in range(0, len(view), piece_bytes):
                     tasks.append((_pread_piece, (path, off, view[off:off + piece_bytes])))
             elif nz == zc:
-                tasks.append((self.read_chunk_into, (index, out[zs].reshape(self.chunks), max(1, workers // len(pieces)))))
+                tasks.append((self.read_chunk_into, (index, window.reshape(self.chunks), max(1, workers // len(cells)))))
             else:                                           # compressed partial chunk: decode, then copy the prefix
-                tasks.append((self._read_partial, (index, out[zs])))
+                tasks.append((self._read_window, (index, window)))
         if pool is None or len(tasks) <= 1:
             return listed + sum(fn(*a) or 0 for fn, a in tasks)
         return listed + sum(f.result() or 0 for f in [pool.submit(fn, *a) for fn, a in tasks])
 
-    def _read_partial(self, index, dest: np.ndarray) -> int:
+    def _read_window(self, index, window: np.ndarray) -> int:
+        """Decode a whole chunk into scratch and copy the part that lies inside the array into ``window``."""
         scratch = np.empty(self.chunks, dtype=self.dtype)
         n = self.read_chunk_into(index, scratch)
-        dest[...] = scratch[0, 0, :dest.shape[0]]
+        window[...] = scratch[0, 0][tuple(slice(0, k) for k in window.shape)]
         return n
 
     def write_stack(self, t: int, c: int, data: np.ndarray, pool=None) -> int:

@@ -90,7 +90,7 @@ def test_reads_sharding_indexed(tmp_path, index_at_end):
     table = np.full((n_inner, 2), 2**64 - 1, dtype="<u8")
     for k, off, n in index:
         table[k] = (off, n)
-    raw_index = table.tobytes() + (zlib.crc32(table.tobytes()) & 0xFFFFFFFF).to_bytes(4, "little")   # value unchecked
+    raw_index = table.tobytes() + zarr_io.crc32c(table.tobytes()).to_bytes(4, "little")
     path = arr.chunk_path((0, 0, 0, 0, 0))
     path.parent.mkdir(parents=True)
     path.write_bytes(body + raw_index if index_at_end else raw_index + body)
@@ -101,6 +101,11 @@ def test_reads_sharding_indexed(tmp_path, index_at_end):
     want = data[0, 0].copy()
     want[2:4] = 0                                              # the missing inner chunk reads as fill_value
     assert np.array_equal(out, want)
+    blob = bytearray(path.read_bytes())                        # a damaged index is refused (crc32c index codec)
+    blob[-10 if index_at_end else 5] ^= 0x40
+    path.write_bytes(bytes(blob))
+    with pytest.raises(IOError, match="checksum"):
+        sharded.read_stack_into(0, 0, out)
 
 
 def test_plate_metadata_roundtrip_and_units(tmp_path):
@@ -135,3 +140,38 @@ def test_deskewed_plate_layout(tmp_path):
     assert arr.shape == (1, 2, 4, 16, 165) and arr.dtype == np.float32
     assert arr.chunks == (1, 1, 4, 16, 165)
     assert dst[0].scale == pytest.approx((1, 1, 3 * 0.5 * 0.116, 0.116, 0.116))
+
+
+@pytest.mark.parametrize("layout", ["raw", "zstd", "sharded"])
+def test_chunks_that_tile_y_and_x(tmp_path, layout):
+    """A writer's default chunking may split the frame: (1, 1, 4, 5, 8) chunks of a (1, 1, 10, 12, 20) array, with
+    partial chunks on every axis; hand-written chunk files (the writer here only emits z-slab chunks)."""
+    if layout == "zstd" and not zarr_io.zstd_available():
+        pytest.skip("libzstd.so.1 not present")
+    shape, chunks = (1, 1, 10, 12, 20), (1, 1, 4, 5, 8)
+    data = _pattern(shape) + (np.arange(12, dtype=np.uint16) * 1000)[None, None, None, :, None]
+    inner = (1, 1, 2, 5, 4) if layout == "sharded" else None
+    codec = zarr_io.Codec("zstd", 3) if layout == "zstd" else zarr_io.Codec()
+    arr = zarr_io.ZarrArray.create(tmp_path / "a", shape, chunks, np.uint16, zstd_level=3 if layout == "zstd" else None,
+                                   shard_inner=inner)
+    for kz in range(3):
+        for ky in range(3):
+            for kx in range(3):
+                block = np.zeros(chunks, np.uint16)
+                part = data[:, :, kz * 4:(kz + 1) * 4, ky * 5:(ky + 1) * 5, kx * 8:(kx + 1) * 8]
+                block[tuple(slice(0, n) for n in part.shape)] = part
+                if layout == "sharded":
+                    arr.write_chunk((0, 0, kz, ky, kx), block)          # shard writer: inner chunks + index + crc32c
+                else:
+                    path = arr.chunk_path((0, 0, kz, ky, kx))
+                    path.parent.mkdir(parents=True, exist_ok=True)
+                    path.write_bytes(bytes(codec.encode(block)))
+    out = np.empty(shape[2:], np.uint16)
+    opened = zarr_io.ZarrArray.open(tmp_path / "a")
+    opened.read_stack_into(0, 0, out)
+    assert np.array_equal(out, data[0, 0])
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(3) as pool:
+        out[:] = 0
+        opened.read_stack_into(0, 0, out, pool=pool)
+    assert np.array_equal(out, data[0, 0])
