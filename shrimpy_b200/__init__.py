@@ -7,7 +7,7 @@ deskew helpers it calls).  Public names mirror the ones shrimPy imports; see
 """
 
 from .deskew import (DeskewGeometry, HostPipeline, deskew_data, deskew_geometry, deskew_window, deskew_zyx,
-                     fast_deskew_zyx, get_deskewed_data_shape, window_needs)
+                     empty_deskewed, fast_deskew_zyx, get_deskewed_data_shape, window_needs)
 from .settings import DeskewSettings
 from . import flatfield, reductions, register  # noqa: E402,F401  (light: torch is imported lazily inside the calls)
 
@@ -21,6 +21,7 @@ __all__ = [
     "deskew_geometry",
     "deskew_window",
     "deskew_zyx",
+    "empty_deskewed",
     "fast_deskew_zyx",
     "get_deskewed_data_shape",
     "window_needs",

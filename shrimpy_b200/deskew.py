@@ -33,6 +33,7 @@ __all__ = [
     "get_deskewed_data_shape",
     "fast_deskew_zyx",
     "deskew_zyx",
+    "empty_deskewed",
     "deskew_data",
     "deskew_window",
     "window_needs",
@@ -155,9 +156,9 @@ def deskew_zyx(raw_data, ls_angle_deg: float, px_to_scan_ratio: float, keep_over
                value_range=None, scale=None):
     """Deskew a CUDA tensor ``(Z, Y, X)`` (uint16 or float32) into float32 ``(ceil(Y/n), X, Xp)``.
 
-    Runs asynchronously on torch's current stream; ``out`` may be a preallocated
-    contiguous float32 tensor of the deskewed shape.  ``value_range``: an optional float32 CUDA tensor
-    of two elements that receives ``(min, max)`` of the deskewed volume, reduced inside the deskew
+    Runs asynchronously on torch's current stream; ``out`` may be a preallocated float32 tensor of the
+    deskewed shape, contiguous or with padded rows (``empty_deskewed``).
+    ``value_range``: an optional float32 CUDA tensor of two elements that receives ``(min, max)`` of the deskewed volume, reduced inside the deskew
     kernel (the range the tracking step needs next, ``shrimpy/dynatrack/tracking.py:583-584``; pass it
     on to ``reductions.percentile(..., value_range=...)``).  ``scale``: optional flat-field scale field
     ``(Y, X)`` applied in the same pass (see ``flatfield.deskew_flat_field_zyx``); only with ``value_range``.
@@ -175,11 +176,15 @@ def deskew_zyx(raw_data, ls_angle_deg: float, px_to_scan_ratio: float, keep_over
         stream = torch.cuda.current_stream().cuda_stream
         if out is None:
             out = torch.empty(g.out_shape, dtype=torch.float32, device=raw.device)
-        elif (tuple(out.shape) != g.out_shape or out.dtype != torch.float32 or not out.is_contiguous()
-              or out.device != raw.device):
-            raise ValueError(f"out must be a contiguous float32 tensor of shape {g.out_shape} on {raw.device}")
+        elif (tuple(out.shape) != g.out_shape or out.dtype != torch.float32 or out.device != raw.device
+              or (out.numel() and (out.stride(2) != 1 or out.stride(1) < g.out_shape[2]
+                                   or out.stride(0) < g.out_shape[1] * out.stride(1)))):
+            raise ValueError(f"out must be a float32 tensor of shape {g.out_shape} on {raw.device} with unit stride along "
+                             "the last axis and non-overlapping rows and planes (see empty_deskewed)")
         if out.numel() == 0:
             return out
+        if not out.is_contiguous() and (value_range is not None or scale is not None):
+            raise ValueError("value_range / scale need a contiguous out")
         fill = _resolve_cval(torch, raw, code, cval, stream)
         Z, Y, X = g.raw_shape
         if value_range is not None:
@@ -198,8 +203,25 @@ def deskew_zyx(raw_data, ls_angle_deg: float, px_to_scan_ratio: float, keep_over
             raise ValueError("scale is only taken together with value_range; use flatfield.deskew_flat_field_zyx")
         _cabi.check(_cabi.lib().shrimpy_deskew_device(
             raw.data_ptr(), code, out.data_ptr(), Z, Y, X, g.out_shape[2], g.n_avg, g.m00, g.m02, g.shift, fill,
-            raw.stride(0), raw.stride(1), 0, 0, _cabi.KERNELS[kernel], stream))
+            raw.stride(0), raw.stride(1), out.stride(0), out.stride(1), _cabi.KERNELS[kernel], stream))
     return out
+
+
+def empty_deskewed(g: DeskewGeometry, device, row_align: int = 8):
+    """Uninitialised float32 tensor of the deskewed shape whose rows start on ``row_align``-float boundaries (default
+    8 floats = one 32-byte DRAM sector): a view ``buf[:, :, :Xp]`` of a buffer with a padded last axis, for ``out=``.
+
+    Why: the deskewed rows are ``Xp`` floats long and ``Xp`` is usually odd (1279 for the mantis FOV), so in a
+    contiguous result every row starts at a different offset inside a sector and the kernel's 128-byte row stores
+    leave partial sectors behind.  Measured on B200 (``tools/probe/padded_out_probe.py``): with padded rows the
+    write-dominated ``average_n_slices=1`` deskews run 0.82 -> 0.64 ms and 1.18 -> 0.88 ms (keep_overhang), the
+    ``n=3`` case 0.301 -> 0.291 ms.  The values are identical; only the strides differ, so a consumer that needs a
+    contiguous tensor should not use this (the copy costs more than it saves).
+    """
+    torch = _torch()
+    P, X, Xp = g.out_shape
+    pitch = -(-Xp // row_align) * row_align
+    return torch.empty((P, X, pitch), dtype=torch.float32, device=device)[:, :, :Xp]
 
 
 def fast_deskew_zyx(raw_data, ls_angle_deg: float, px_to_scan_ratio: float, keep_overhang: bool,
