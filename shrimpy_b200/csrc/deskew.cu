@@ -290,7 +290,15 @@ constexpr int kMaxTmaAvg = 4;   // template instantiations exist for n = 1..4
 // RANGE: the value range of the written voxels is reduced in the same pass (per thread -> warp shuffle -> CTA ->
 // one atomicMin / atomicMax pair per CTA on ordered keys): the min/max pass the tracking step makes right after
 // the deskew (shrimpy/dynatrack/tracking.py:583-584) disappears.
-template <typename T, int NAVG, bool SCALED, bool RANGE>
+//
+// ALIGNED (opt-in, SHRIMPY_KERNEL_TMA_ALIGNED): whole-sector row spans for contiguous outputs whose row length is not a
+// multiple of 8 floats.  Tiles advance by T2 - 8 columns while the 256 threads still cover T2, so neighbouring tiles
+// overlap by 8 columns; every 32-byte sector of an output row is stored by exactly ONE tile -- the tile that holds the
+// column of the sector's first float (clamped to the window's first column) -- and the overlap voxels are computed
+// twice but stored once.  Only the first and last warp of a tile's o2 span ever skip a store; their test is three
+// integer instructions on the store address.  `tools/sector_spans.py` mirrors the rule and `tests/test_sector_spans.py`
+// proves on the CPU that every voxel has exactly one owner.
+template <typename T, int NAVG, bool SCALED, bool RANGE, bool ALIGNED = false>
 __global__ void __launch_bounds__(kTmaThreads, 4)
     deskew_tma_kernel(const __grid_constant__ CUtensorMap tmap, const DeskewParams P) {
     constexpr int EPC = Chunk<T>::kElems;
@@ -311,7 +319,8 @@ __global__ void __launch_bounds__(kTmaThreads, 4)
     const int t2 = blockIdx.x / P.tiles_x;
     const int p = P.p0 + blockIdx.y;
     const int x0 = tx * TX;
-    const int c0 = P.cbeg + t2 * P.T2;
+    const int step2 = ALIGNED ? P.T2 - 8 : P.T2;   // columns between the first columns of neighbouring tiles
+    const int c0 = P.cbeg + t2 * step2;
     const int c_last = min(c0 + P.T2, P.cend) - 1;
     const double zmax = (double)(P.Z - 1);
 
@@ -402,6 +411,14 @@ __global__ void __launch_bounds__(kTmaThreads, 4)
     const long long row_bytes = P.out_s1 * (long long)sizeof(float);
     float vlo = 3.402823466e38f, vhi = -3.402823466e38f;
 
+    // ALIGNED: a = (address / 4) & 7 is the voxel's place inside its sector, t - a the tile-local column of the
+    // sector's first float.  The tile owns the sector iff 0 <= t - a < step2 (tile 0 also owns t - a < 0):
+    // store iff own_lo < a <= own_hi.  Only threads with t < 8 or t >= step2 can fail the test.
+    const int t_local = (warp % warps_o2) * 32 + lane;
+    const int own_hi = (!ALIGNED || t2 == 0) ? 7 : min(t_local, 7);
+    const int own_lo = ALIGNED ? t_local - step2 : -1;
+    const bool edge_warp = ALIGNED && ((warp % warps_o2) == 0 || (warp % warps_o2) == warps_o2 - 1);
+
     for (int c = part; c < 8; c += parts) {
         float r[EPC];
         if (warp_all_in) {
@@ -442,7 +459,14 @@ __global__ void __launch_bounds__(kTmaThreads, 4)
             const int xc = x0 + c * EPC;
             const int xvalid = P.X - xc;  // elements of this chunk that exist (uniform over the CTA)
             char *ptr = out_col + (long long)(P.X - 1 - xc) * row_bytes;
-            if (xvalid >= EPC) {
+            if (ALIGNED && (edge_warp || xvalid < EPC)) {
+#pragma unroll
+                for (int j = 0; j < EPC; ++j) {
+                    const int a = (int)((reinterpret_cast<uintptr_t>(ptr) >> 2) & 7u);
+                    if (j < xvalid && a > own_lo && a <= own_hi) __stcs(reinterpret_cast<float *>(ptr), r[j]);
+                    ptr -= row_bytes;
+                }
+            } else if (xvalid >= EPC) {
 #pragma unroll
                 for (int j = 0; j < EPC; ++j) {
                     __stcs(reinterpret_cast<float *>(ptr), r[j]);   // streaming: outputs are never re-read
@@ -527,9 +551,10 @@ static int launch_direct(const DeskewParams &Pin, cudaStream_t stream) {
 }
 
 template <typename T, int NAVG>
-static int launch_tma_n(const CUtensorMap &tmap, const DeskewParams &P, size_t smem, cudaStream_t stream) {
+static int launch_tma_n(const CUtensorMap &tmap, const DeskewParams &P, size_t smem, cudaStream_t stream, bool aligned) {
     auto kern = P.scale ? (P.range ? deskew_tma_kernel<T, NAVG, true, true> : deskew_tma_kernel<T, NAVG, true, false>)
                         : (P.range ? deskew_tma_kernel<T, NAVG, false, true> : deskew_tma_kernel<T, NAVG, false, false>);
+    if (aligned) kern = deskew_tma_kernel<T, NAVG, false, false, true>;   // launch_tma admits it without scale / range only
     if (smem + 1024 > 48 * 1024)  // static smem counts against the 48 KB default as well
         SHRIMPY_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<dim3((unsigned)((long long)P.tiles_x * P.tiles_o2), (unsigned)P.pcount), kTmaThreads, smem, stream>>>(tmap, P);
@@ -541,7 +566,7 @@ static int launch_tma_n(const CUtensorMap &tmap, const DeskewParams &P, size_t s
 // Returns SHRIMPY_OK and sets *used = true when the TMA kernel was launched; *used = false
 // (still SHRIMPY_OK) when the problem is not eligible and the caller should fall back.
 template <typename T>
-static int launch_tma(const DeskewParams &Pin, cudaStream_t stream, bool *used, bool required) {
+static int launch_tma(const DeskewParams &Pin, cudaStream_t stream, bool *used, bool required, bool aligned = false) {
     *used = false;
     DeskewParams P = Pin;
     constexpr int ES = (int)sizeof(T);
@@ -553,6 +578,7 @@ static int launch_tma(const DeskewParams &Pin, cudaStream_t stream, bool *used, 
     else if ((P.raw_sy * ES) % 16 != 0 || (P.raw_sz * ES) % 16 != 0) why = "raw strides not multiples of 16 bytes";
     else if (P.raw_sy < P.X || P.raw_sz < (long long)P.y_cnt * P.raw_sy) why = "raw strides overlap";
     else if (P.pcount > 65535) why = "too many tilt blocks for grid.y";
+    else if (aligned && (P.scale || P.range)) why = "whole-sector spans are not built for the fused scale / value range";
 
     if (!why) {
         // Tile extent along o2: the staged scan range must fit nz_cap <= 256 slices and the CTA's
@@ -579,7 +605,8 @@ static int launch_tma(const DeskewParams &Pin, cudaStream_t stream, bool *used, 
         return SHRIMPY_OK;
     }
     P.tiles_x = (P.X + TX - 1) / TX;
-    P.tiles_o2 = (P.cend - P.cbeg + P.T2 - 1) / P.T2;
+    const int step2 = aligned ? P.T2 - 8 : P.T2;
+    P.tiles_o2 = (P.cend - P.cbeg + step2 - 1) / step2;
     if ((long long)P.tiles_x * P.tiles_o2 > 2147483647LL) {
         if (required) return fail(SHRIMPY_EINVAL, "deskew: grid too large");
         return SHRIMPY_OK;
@@ -603,10 +630,10 @@ static int launch_tma(const DeskewParams &Pin, cudaStream_t stream, bool *used, 
     const size_t smem = (size_t)P.nz_cap * kRowBytes * P.n + 1024;
     int err;
     switch (P.n) {
-        case 1: err = launch_tma_n<T, 1>(tmap, P, smem, stream); break;
-        case 2: err = launch_tma_n<T, 2>(tmap, P, smem, stream); break;
-        case 3: err = launch_tma_n<T, 3>(tmap, P, smem, stream); break;
-        default: err = launch_tma_n<T, 4>(tmap, P, smem, stream); break;
+        case 1: err = launch_tma_n<T, 1>(tmap, P, smem, stream, aligned); break;
+        case 2: err = launch_tma_n<T, 2>(tmap, P, smem, stream, aligned); break;
+        case 3: err = launch_tma_n<T, 3>(tmap, P, smem, stream, aligned); break;
+        default: err = launch_tma_n<T, 4>(tmap, P, smem, stream, aligned); break;
     }
     if (err == SHRIMPY_OK) *used = true;
     return err;
@@ -616,7 +643,8 @@ template <typename T>
 static int deskew_dispatch(const DeskewParams &P, int kernel, cudaStream_t stream) {
     if (kernel != SHRIMPY_KERNEL_DIRECT) {
         bool used = false;
-        const int err = launch_tma<T>(P, stream, &used, kernel == SHRIMPY_KERNEL_TMA);
+        const bool aligned = kernel == SHRIMPY_KERNEL_TMA_ALIGNED;
+        const int err = launch_tma<T>(P, stream, &used, kernel == SHRIMPY_KERNEL_TMA || aligned, aligned);
         if (err != SHRIMPY_OK || used) return err;
     }
     return launch_direct<T>(P, stream);
@@ -674,7 +702,7 @@ static int deskew_window_impl(const void *d_raw, int raw_dtype, float *d_out, in
         return fail(SHRIMPY_EINVAL, "deskew: bad shape Z=%d Y=%d X=%d Xp=%d n=%d", Z, Y, X, Xp, n_avg);
     if (raw_dtype != SHRIMPY_U16 && raw_dtype != SHRIMPY_F32)
         return fail(SHRIMPY_EINVAL, "deskew: raw_dtype must be SHRIMPY_U16 or SHRIMPY_F32, got %d", raw_dtype);
-    if (kernel < SHRIMPY_KERNEL_AUTO || kernel > SHRIMPY_KERNEL_TMA)
+    if (kernel < SHRIMPY_KERNEL_AUTO || kernel > SHRIMPY_KERNEL_TMA_ALIGNED)
         return fail(SHRIMPY_EINVAL, "deskew: unknown kernel selector %d", kernel);
     if (!std::isfinite(m00) || !std::isfinite(m02) || !std::isfinite(shift))
         return fail(SHRIMPY_EINVAL, "deskew: non-finite affine row");

@@ -271,3 +271,20 @@ def test_padded_row_output_is_the_same_volume(torch, sb, n, keep, kernel):
         sb.deskew_zyx(raw, 30.0, 0.39, keep, n, out=out.transpose(1, 2))
     with pytest.raises(ValueError):
         sb.deskew_zyx(raw, 30.0, 0.39, keep, n, out=out, value_range=torch.empty(2, device="cuda"))
+
+
+@pytest.mark.skipif(not __import__("os").environ.get("SHRIMPY_TEST_UNMEASURED"),
+                    reason="kernel='tma_aligned' was written after round 1's GPU minutes ran out: first run "
+                           "tools/probe/aligned_rows_probe.py on a B200, then drop this gate")
+@pytest.mark.parametrize("shape,r,keep,n", [((90, 13, 128), 0.39, False, 1), ((120, 31, 200), 0.39, True, 3),
+                                            ((120, 31, 200), 0.651, False, 4), ((300, 40, 264), 1.3, True, 1)])
+def test_whole_sector_spans_variant_is_the_same_volume(torch, sb, shape, r, keep, n):
+    """``SHRIMPY_KERNEL_TMA_ALIGNED``: overlapping o2 tiles, every 32-byte sector of a row stored by one tile
+    (rule proven on the host mirror in tests/test_sector_spans.py).  Same voxels, nothing else touched."""
+    raw = torch.from_numpy(synthetic_stack(shape, seed=6)).cuda()
+    want = sb.deskew_zyx(raw, 30.0, r, keep, n, kernel="tma")
+    got = torch.full_like(want, -7.0)
+    sb.deskew_zyx(raw, 30.0, r, keep, n, out=got, kernel="tma_aligned")
+    assert torch.equal(got, want)
+    with pytest.raises(Exception):
+        sb.deskew_zyx(raw, 30.0, r, keep, n, kernel="tma_aligned", value_range=torch.empty(2, device="cuda"))

@@ -1,0 +1,87 @@
+"""Whole-sector row spans in the CONTIGUOUS result (``kernel="tma_aligned"``, csrc/deskew.cu ALIGNED) against the plain
+TMA kernel: first bit equality on awkward shapes (windows that start inside a sector, ragged X tiles, padded rows, every
+n), then the config-2 / n=1 / config-5-like timings next to the padded-row figures of ``padded_out_probe.py``.
+
+    python tools/probe/aligned_rows_probe.py > gpurun_out/aligned_rows_probe.json
+
+Written without a GPU at hand (round 1 ran out of GPU minutes): nothing selects this kernel until this probe has shown
+equality and a gain on a B200.
+"""
+import json
+import sys
+from pathlib import Path
+
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent.parent))
+import torch
+
+import shrimpy_b200 as sb
+
+res = {"equal": {}, "ms": {}}
+gen = torch.Generator(device="cuda").manual_seed(7)
+
+
+def stack(shape, dtype=torch.uint16):
+    t = torch.randint(100, 60000, shape, dtype=torch.int32, device="cuda", generator=gen)
+    return t.to(dtype)
+
+
+# ---- equality ---------------------------------------------------------------------------------------------------
+for shape, r, keep, n, dtype in [((90, 13, 128), 0.39, False, 1, torch.uint16), ((90, 13, 128), 0.39, True, 2, torch.uint16),
+                                 ((120, 31, 200), 0.39, True, 3, torch.uint16), ((120, 31, 200), 0.651, False, 4, torch.uint16),
+                                 ((75, 17, 96), 0.39, True, 1, torch.float32), ((300, 40, 264), 1.3, True, 1, torch.uint16),
+                                 ((600, 30, 512), 0.39, False, 3, torch.uint16)]:
+    raw = stack(shape, dtype)
+    g = sb.deskew_geometry(shape, 30.0, r, keep, n)
+    want = sb.deskew_zyx(raw, 30.0, r, keep, n, kernel="tma")
+    key = f"{shape}_r{r}_keep{int(keep)}_n{n}_{str(dtype)[6:]}"
+    got = torch.full_like(want, -7.0)
+    sb.deskew_zyx(raw, 30.0, r, keep, n, out=got, kernel="tma_aligned")
+    res["equal"][key] = bool(torch.equal(got, want))
+    padded = sb.empty_deskewed(g, raw.device)
+    sb.deskew_zyx(raw, 30.0, r, keep, n, out=padded, kernel="tma_aligned")
+    res["equal"][key + "_padded_rows"] = bool(torch.equal(padded, want))
+    # windows that start inside a sector, written into a strided view of a canvas that must stay untouched elsewhere
+    P, X, Xp = g.out_shape
+    canvas = torch.full((P, X, Xp), -7.0, device="cuda")
+    for c0, c1 in ((3, min(Xp, 3 + 61)), (Xp // 3 + 1, Xp - 2)):
+        if c1 <= c0:
+            continue
+        _, zr = sb.window_needs(g, 0, P, c0, c1 - c0)
+        z0, z1 = (int(zr[0]), int(zr[1])) if zr[1] > zr[0] else (0, 1)
+        sb.deskew_window(raw[z0:z1], g, p_begin=0, p_count=P, c_begin=c0, c_count=c1 - c0, y_origin=0, z_origin=z0,
+                         out=canvas[:, :, c0:c1], kernel="tma_aligned")
+        ok = torch.equal(canvas[:, :, c0:c1], want[:, :, c0:c1])
+        canvas[:, :, c0:c1] = -7.0
+        res["equal"][key + f"_window{c0}_{c1}"] = bool(ok and bool((canvas == -7.0).all()))
+    del raw, want, got, padded, canvas
+
+# ---- timings ----------------------------------------------------------------------------------------------------
+def time_it(raw, keep, n, kernel, out, reps=10):
+    for _ in range(3):
+        sb.deskew_zyx(raw, 30.0, 0.39, keep, n, out=out, kernel=kernel)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        sb.deskew_zyx(raw, 30.0, 0.39, keep, n, out=out, kernel=kernel)
+    b.record()
+    torch.cuda.synchronize()
+    return round(a.elapsed_time(b) / reps, 4)
+
+
+if all(res["equal"].values()):
+    raw = stack((600, 300, 2048))
+    for n, keep in ((1, False), (1, True), (2, False), (3, False), (4, False)):
+        g = sb.deskew_geometry((600, 300, 2048), 30.0, 0.39, keep, n)
+        out = torch.empty(g.out_shape, dtype=torch.float32, device="cuda")
+        for kernel in ("tma", "tma_aligned"):
+            res["ms"][f"n{n}_keep{int(keep)}_{kernel}_contiguous"] = time_it(raw, keep, n, kernel, out)
+        del out
+        res["ms"][f"n{n}_keep{int(keep)}_tma_padded_rows"] = time_it(raw, keep, n, "tma", sb.empty_deskewed(g, "cuda"))
+    del raw
+    raw = stack((4000, 300, 2048))                           # config 5 on one GPU: 25.9 GB of output
+    g = sb.deskew_geometry((4000, 300, 2048), 30.0, 0.39, True, 1)
+    out = torch.empty(g.out_shape, dtype=torch.float32, device="cuda")
+    for kernel in ("tma", "tma_aligned"):
+        res["ms"][f"config5_{kernel}_contiguous"] = time_it(raw, True, 1, kernel, out, reps=5)
+print(json.dumps(res, indent=1))
+sys.exit(0 if all(res["equal"].values()) else 1)
