@@ -372,4 +372,21 @@ def deskew_data(raw_data: np.ndarray, ls_angle_deg: float, px_to_scan_ratio: flo
     if math.prod(g.out_shape) == 0:
         return np.empty(g.out_shape, dtype=np.float32)
     fill = float(raw.min()) if cval is None else float(cval)
+    if out is None:
+        out = _empty_pinned_result(torch, g.out_shape)
     return _pipeline_for(dev.index).deskew(raw, g, fill, out)
+
+
+def _empty_pinned_result(torch, shape) -> np.ndarray:
+    """Result array of a numpy-in/numpy-out call, taken from torch's caching pinned-host allocator.
+
+    The device-to-host copy is the stage that bounds the host path and it only runs
+    asynchronously, at the full PCIe rate, into page-locked memory; a pageable ``np.empty`` would make every slab's copy
+    a staged, blocking one.  The array is an ordinary float32 ndarray whose base keeps the block alive; when the caller
+    drops it the block returns to torch's cache, so a loop over chunks or positions pins memory once.  Falls back to
+    pageable memory when the host refuses to lock that much.
+    """
+    try:
+        return torch.empty(tuple(shape), dtype=torch.float32, pin_memory=True).numpy()
+    except RuntimeError:
+        return np.empty(shape, dtype=np.float32)
