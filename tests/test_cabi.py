@@ -98,3 +98,15 @@ def test_no_cpu_path():
         sb.deskew_data(np.zeros((4, 4, 8), np.uint16), 30.0, 0.39, True)
     with pytest.raises(RuntimeError):
         sb.fast_deskew_zyx(torch.zeros((4, 4, 8)), 30.0, 0.39, True)
+
+
+def test_host_result_allocation_falls_back_to_pageable_memory():
+    """``deskew_data`` takes its result from torch's pinned-host cache; a host that cannot lock the pages (here: no
+    CUDA runtime at all) gets an ordinary array of the same shape and dtype."""
+    import torch
+
+    from shrimpy_b200.deskew import _empty_pinned_result
+
+    out = _empty_pinned_result(torch, (3, 4, 5))
+    assert isinstance(out, np.ndarray) and out.dtype == np.float32 and out.shape == (3, 4, 5)
+    assert out.flags.c_contiguous and out.flags.writeable
