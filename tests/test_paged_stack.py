@@ -1,0 +1,147 @@
+"""Byte-paged scan split (``shrimpy_b200/paged_stack.py``) on CPU: the layout arithmetic, a host stand-in for the
+stitched window (same ``slices`` / ``fill_own`` code as the CUDA class) driven through the numpy window kernel, and the
+file-descriptor hand-over between processes.  The CUDA driver calls themselves need GPUs (tools/scan_split_bench.py
+--transport vmm)."""
+
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+import shrimpy_b200 as sb
+from helpers import synthetic_stack
+from oracle import deskew_oracle as o
+from shrimpy_b200 import paged_stack as ps
+from test_sharding import numpy_window
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 4, 8])
+@pytest.mark.parametrize("keep", [True, False])
+@pytest.mark.parametrize("granularity", [2 << 20, 64 << 10])
+def test_plan_partitions_the_stack_into_pages_and_maps_every_needed_byte(world, keep, granularity):
+    g = sb.deskew_geometry((4000, 300, 2048), 30.0, 0.39, keep, 1)          # BASELINE configs[4] geometry
+    F = 300 * 2048 * 2
+    shards = ps.plan_paged_split(g, world, F, granularity)
+    total = -(-4000 * F // granularity) * granularity
+    assert shards[0].own_bytes[0] == 0 and shards[-1].own_bytes[1] == total
+    assert shards[0].cols[0] == 0 and shards[-1].cols[1] == g.out_shape[2]
+    for a, b in zip(shards[:-1], shards[1:]):
+        assert a.own_bytes[1] == b.own_bytes[0] and a.cols[1] == b.cols[0]
+    for s in shards:
+        assert all(v % granularity == 0 for v in s.own_bytes + s.window_bytes) and s.stack_bytes == 4000 * F
+        wlo, whi = s.window_bytes
+        if s.need_z[1] > s.need_z[0]:
+            assert wlo <= s.need_z[0] * F and s.need_z[1] * F <= whi          # every byte the columns read is visible
+        assert wlo <= s.own_bytes[0] and s.own_bytes[1] <= whi                # and everything the rank has to load
+        # the maps tile the window in order, without gaps, from inside each owner's pages
+        at = 0
+        for owner, h_off, w_off, size in s.maps:
+            assert w_off == at and size > 0 and size % granularity == 0 and h_off % granularity == 0
+            lo, hi = shards[owner].own_bytes
+            assert lo + h_off == wlo + w_off and lo + h_off + size <= hi
+            at += size
+        assert at == whi - wlo
+        if world > 1:
+            # the halo: about r*cos(theta)*(Y-1)+1 slices below, two above, rounded out to pages
+            assert s.remote_bytes <= (int(0.39 * np.cos(np.pi / 6) * 299) + 5) * F + 3 * granularity
+
+
+class HostPagedStack(ps.PagedWindow):
+    """Stand-in for ``PagedStack``: every rank's pages are numpy bytes, the window is stitched by copying them in the
+    order of ``shard.maps`` (what ``cuMemMap`` does with address translation)."""
+
+    def __init__(self, shards, rank, frame_shape, dtype, pages_of_rank):
+        self.shards, self.rank, self.shard = shards, rank, shards[rank]
+        self.frame_shape, self.dtype = tuple(frame_shape), dtype
+        self.frame_bytes = frame_shape[0] * frame_shape[1] * torch.empty((), dtype=dtype).element_size()
+        wlo, whi = self.shard.window_bytes
+        window = np.zeros(whi - wlo, dtype=np.uint8)
+        for owner, h_off, w_off, size in self.shard.maps:
+            window[w_off:w_off + size] = pages_of_rank[owner][h_off:h_off + size]
+        self._window = torch.from_numpy(window)
+        lo, hi = self.shard.own_bytes
+        self.own = self._window[lo - wlo:hi - wlo]
+
+
+@pytest.mark.parametrize("params,world,granularity", [
+    (((120, 13, 8), 30.0, 0.39, True, 1), 3, 64),        # pages far smaller than a slice (13*8*2 = 208 B)
+    (((150, 10, 8), 30.0, 0.39, False, 3), 2, 4096),     # pages of ~25 slices
+    (((60, 9, 16), 30.0, 0.39, True, 2), 4, 1 << 20),    # one page holds the whole stack: rank 0 owns it all
+], ids=["small-pages", "medium-pages", "one-page"])
+def test_stitched_windows_deskew_like_the_whole_stack(params, world, granularity):
+    shape, ang, r, keep, n = params
+    raw = synthetic_stack(shape, seed=21)
+    g = sb.deskew_geometry(shape, ang, r, keep, n)
+    F = shape[1] * shape[2] * 2
+    shards = ps.plan_paged_split(g, world, F, granularity, align=8)
+    flat = np.zeros(shards[-1].own_bytes[1], dtype=np.uint8)
+    flat[:raw.nbytes] = raw.reshape(-1).view(np.uint8)
+    # every rank loads its own pages through fill_own (slices in, bytes out) ...
+    pages = []
+    for s in shards:
+        loader = HostPagedStack(shards, s.rank, shape[1:], torch.uint16,
+                                [np.zeros(t.own_bytes[1] - t.own_bytes[0], np.uint8) for t in shards])
+        loader.fill_own(lambda z0, z1: torch.from_numpy(raw[z0:z1].copy()))
+        mine = loader.own.numpy().copy()
+        valid = min(s.own_bytes[1], raw.nbytes) - s.own_bytes[0]
+        assert np.array_equal(mine[:max(valid, 0)], flat[s.own_bytes[0]:s.own_bytes[0] + max(valid, 0)])
+        pages.append(mine)
+    # ... and deskews its columns in one window call over the stitched range
+    pieces = []
+    for s in shards:
+        stack = HostPagedStack(shards, s.rank, shape[1:], torch.uint16, pages)
+        if s.need_z[1] > s.need_z[0]:
+            assert np.array_equal(stack.slices(*s.need_z).numpy(), raw[s.need_z[0]:s.need_z[1]])
+        with pytest.raises(ValueError):
+            stack.slices(0, shape[0] + 10**6)
+        pieces.append(ps.deskew_paged_split(stack, g, s, cval=-3.0, window_fn=numpy_window).numpy())
+    got = np.concatenate(pieces, axis=2)
+    whole = o.deskew_data(raw, ang, r, keep, n, cval=-3.0)
+    assert got.shape == whole.shape
+    assert np.array_equal(got == -3.0, whole == -3.0)
+    assert np.max(np.abs(got - whole)) <= 2e-6 * float(whole.max() - whole.min())
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _fd_worker(rank, world, port, outdir):
+    import torch.distributed as dist
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        g = sb.deskew_geometry((4000, 30, 64), 30.0, 0.39, True, 1)
+        shards = ps.plan_paged_split(g, world, 30 * 64 * 2, 64 << 10)
+        fd = os.memfd_create(f"pages{rank}")            # stands for the exported CUDA allocation handle
+        os.write(fd, f"pages of rank {rank}".encode())
+        got = ps.exchange_descriptors(fd, shards, rank)
+        assert sorted(got) == sorted(owner for owner, _, _, _ in shards[rank].maps if owner != rank)
+        for owner, peer_fd in got.items():
+            assert os.pread(peer_fd, 64, 0) == f"pages of rank {owner}".encode()
+            os.close(peer_fd)
+        os.close(fd)
+        with open(os.path.join(outdir, f"ok{rank}"), "w") as f:
+            f.write(str(len(got)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_descriptor_hand_over_world3(tmp_path):
+    world = 3
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    procs = [ctx.Process(target=_fd_worker, args=(r, world, port, str(tmp_path))) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=180)
+        assert p.exitcode == 0
+    counts = [int((tmp_path / f"ok{r}").read_text()) for r in range(world)]
+    assert counts == [1, 2, 1]          # the middle rank maps both neighbours, the ends one each

@@ -18,3 +18,6 @@ run aligned_rows_test    120 env SHRIMPY_TEST_UNMEASURED=1 python -m pytest test
 run host_call_probe      300 python tools/probe/host_call_probe.py
 run bench                600 python bench.py
 tail -n 3 gpurun_out/*.out | cut -c1-400
+# then, in a 2-GPU call (gpurun --gpus 2), the scan split with no exchange step (paged_stack.py) beside the measured one:
+#   for t in peer vmm; do python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
+#       --master-port 29611 tools/scan_split_bench.py --transport $t > gpurun_out/scan_split_$t.json 2> gpurun_out/scan_split_$t.err; done

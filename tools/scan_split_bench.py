@@ -26,8 +26,9 @@ def main():
     ap.add_argument("--shape", default="4000,300,2048")
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--check", type=int, default=1)
-    ap.add_argument("--transport", choices=["nccl", "peer"], default="nccl",
-                    help="halo exchange: NCCL send/recv, or device copies out of peer-mapped (symmetric) memory")
+    ap.add_argument("--transport", choices=["nccl", "peer", "vmm"], default="nccl",
+                    help="halo exchange: NCCL send/recv; device copies out of peer-mapped (symmetric) memory; or none at "
+                         "all -- the neighbours' pages mapped next to the rank's own (paged_stack.py), one launch")
     args = ap.parse_args()
     shape = tuple(int(v) for v in args.shape.split(","))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -50,6 +51,26 @@ def main():
 
     own = slab_of(rank)
     side = None
+    stack = None
+    if args.transport == "vmm":
+        from shrimpy_b200 import paged_stack
+
+        frame_bytes = shape[1] * shape[2] * 2
+        page = paged_stack.PagedStack.granularity(local)
+        pshards = paged_stack.plan_paged_split(g, world, frame_bytes, page)
+        stack = paged_stack.PagedStack(pshards, rank, shape[1:], torch.uint16, local, page)
+
+        def slices_of(z0, z1):   # the same per-rank slabs as the other transports, cut where the pages are
+            parts = []
+            for r in range(world):
+                a, b = shards[r].own_z
+                lo, hi = max(a, z0), min(b, z1)
+                if hi > lo:
+                    parts.append((own if r == rank else slab_of(r))[lo - a:hi - a])
+            return torch.cat(parts, dim=0)
+
+        stack.fill_own(slices_of)
+        stack.barrier()          # every rank's pages are in place before anyone reads them
     if args.transport == "peer":
         peer = sharding.PeerSlab(shards, rank, shape[1:], torch.uint16, torch.device("cuda", local))
         peer.tensor.copy_(own)
@@ -58,8 +79,13 @@ def main():
         peer.barrier()          # every rank's slices are in place before anyone pulls
         torch.cuda.synchronize()
         side = torch.cuda.Stream()
+    def run():
+        if stack is not None:
+            return paged_stack.deskew_paged_split(stack, g, pshards[rank])
+        return sharding.deskew_scan_split(own, g, shards, rank, peer_stream=side)
+
     # warm-up (also builds NCCL channels)
-    piece = sharding.deskew_scan_split(own, g, shards, rank, peer_stream=side)
+    piece = run()
     torch.cuda.synchronize()
     dist.barrier()
     times = []
@@ -68,7 +94,7 @@ def main():
         torch.cuda.synchronize()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        piece = sharding.deskew_scan_split(own, g, shards, rank, peer_stream=side)
+        piece = run()
         b.record()
         torch.cuda.synchronize()
         t = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device="cuda")
@@ -86,6 +112,8 @@ def main():
         if rank == 0 and world == 1:
             pass
     halo = (me.halo_below[1] - me.halo_below[0] + me.halo_above[1] - me.halo_above[0]) * shape[1] * shape[2] * 2
+    if stack is not None:
+        halo = pshards[rank].remote_bytes      # whole pages of the neighbours mapped into this rank's window
     halos = torch.tensor([halo], dtype=torch.float64, device="cuda")
     dist.all_reduce(halos, op=dist.ReduceOp.MAX)
     if rank == 0:
@@ -99,6 +127,9 @@ def main():
                           "interior_cols_frac": round(sum(s.interior_cols[1] - s.interior_cols[0] for s in shards) / g.out_shape[2], 3)}),
               flush=True)
     dist.barrier()
+    if stack is not None:
+        del piece
+        stack.close()
     dist.destroy_process_group()
 
 
