@@ -33,7 +33,8 @@ from typing import Dict, List, Sequence, Tuple
 from .deskew import DeskewGeometry
 from .sharding import plan_scan_split
 
-__all__ = ["PagedShard", "plan_paged_split", "exchange_descriptors", "PagedWindow", "PagedStack", "deskew_paged_split"]
+__all__ = ["PagedShard", "plan_paged_split", "exchange_descriptors", "PagedWindow", "PagedStack", "DeviceSlab",
+           "deskew_paged_split"]
 
 
 @dataclass(frozen=True)
@@ -145,6 +146,20 @@ class _DeviceBytes:
                                          "version": 2, "strides": None}
 
 
+class DeviceSlab:
+    """A contiguous ``(nz, Y, X)`` array in device address space, described the way ``deskew_window`` reads a tensor
+    (``data_ptr``, ``shape``, ``stride``, ``dtype``, ``device``) without being one."""
+
+    def __init__(self, ptr: int, shape: Tuple[int, int, int], dtype, device):
+        self._ptr, self.shape, self.dtype, self.device = int(ptr), tuple(shape), dtype, device
+
+    def data_ptr(self) -> int:
+        return self._ptr
+
+    def stride(self, axis: int) -> int:
+        return (self.shape[1] * self.shape[2], self.shape[2], 1)[axis]
+
+
 def _ck(result, what: str):
     """cuda-python returns ``(CUresult, values...)``; raise on anything but success, return the values."""
     err, rest = result[0], result[1:]
@@ -192,7 +207,8 @@ class PagedStack(PagedWindow):
 
     ``own``     uint8 tensor over the bytes this rank holds (``shard.own_bytes`` of the flattened stack): the loader's
                 destination.  Call ``barrier()`` after filling it and before any rank computes.
-    ``slices``  ``(z1 - z0, Y, X)`` tensor of raw slices inside the window, at one base address, whoever holds them.
+    ``slices``  raw slices inside the window as one ``(z1 - z0, Y, X)`` array at one base address, whoever holds them
+                (a ``DeviceSlab``: an address and a shape, which is all the window kernel takes from a tensor).
     """
 
     def __init__(self, shards: Sequence[PagedShard], rank: int, frame_shape: Tuple[int, int], dtype, device_index: int,
@@ -237,9 +253,27 @@ class PagedStack(PagedWindow):
         except BaseException:
             self.close()
             raise
-        self._window = (torch.as_tensor(_DeviceBytes(self._va, whi - wlo), device=f"cuda:{self.device_index}")
-                        if self._va is not None else torch.empty(0, dtype=torch.uint8, device="cuda"))
-        self.own = self._window[lo - wlo:hi - wlo]
+        # torch only ever aliases the rank's OWN pages (local physical memory: the pointer's device is this one).  A
+        # tensor over the whole window would start in a neighbour's pages, torch would attribute it to that GPU and
+        # ``device=`` would then mean a copy; the window is handed to the kernels as a raw address (``DeviceSlab``).
+        self.own = (torch.as_tensor(_DeviceBytes(self._va + (lo - wlo), hi - lo), device=f"cuda:{self.device_index}")
+                    if hi > lo else torch.empty(0, dtype=torch.uint8, device=f"cuda:{self.device_index}"))
+        if hi > lo and self.own.data_ptr() != self._va + (lo - wlo):
+            self.close()
+            raise RuntimeError("torch copied the mapped pages instead of aliasing them")
+
+    @property
+    def device(self):
+        return self._torch.device("cuda", self.device_index)
+
+    def slices(self, z0: int, z1: int) -> "DeviceSlab":
+        """Raw slices ``[z0, z1)`` of the window as one ``(z1 - z0, Y, X)`` array at one address (remote pages are read
+        over NVLink); accepted by ``deskew_window`` in place of a tensor."""
+        wlo, whi = self.shard.window_bytes
+        a, b = z0 * self.frame_bytes - wlo, z1 * self.frame_bytes - wlo
+        if z1 < z0 or a < 0 or b > whi - wlo or self._va is None:
+            raise ValueError(f"slices [{z0},{z1}) lie outside this rank's window")
+        return DeviceSlab(self._va + a, (z1 - z0,) + self.frame_shape, self.dtype, self.device)
 
     @staticmethod
     def allocation_prop(device_index: int):
@@ -273,7 +307,7 @@ class PagedStack(PagedWindow):
 
     def close(self) -> None:
         drv = self._drv
-        self.own = self._window = None
+        self.own = None
         for ptr, size in self._mapped:
             drv.cuMemUnmap(ptr, size)
         self._mapped = []

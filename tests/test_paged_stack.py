@@ -145,3 +145,10 @@ def test_descriptor_hand_over_world3(tmp_path):
         assert p.exitcode == 0
     counts = [int((tmp_path / f"ok{r}").read_text()) for r in range(world)]
     assert counts == [1, 2, 1]          # the middle rank maps both neighbours, the ends one each
+
+
+def test_device_slab_describes_a_contiguous_stack_like_a_tensor():
+    slab = ps.DeviceSlab(0x7f0000000000, (5, 13, 8), torch.uint16, torch.device("cpu"))
+    like = torch.empty((5, 13, 8), dtype=torch.uint16)
+    assert slab.shape == tuple(like.shape) and slab.dtype == like.dtype
+    assert [slab.stride(i) for i in range(3)] == list(like.stride()) and slab.data_ptr() == 0x7f0000000000
