@@ -212,7 +212,7 @@ class PagedStack(PagedWindow):
     """
 
     def __init__(self, shards: Sequence[PagedShard], rank: int, frame_shape: Tuple[int, int], dtype, device_index: int,
-                 granularity: int, group=None):
+                 granularity: int, group=None, _local_handles=None):
         import torch
         from cuda.bindings import driver as drv
 
@@ -222,6 +222,8 @@ class PagedStack(PagedWindow):
         self.itemsize = torch.empty((), dtype=dtype).element_size()
         self.frame_bytes = self.frame_shape[0] * self.frame_shape[1] * self.itemsize
         self._handles: Dict[int, object] = {}
+        self._release: List[int] = []          # the handles this object has to release (all but borrowed ones)
+        self._local = _local_handles is not None
         self._fds: List[int] = []
         self._va, self._mapped = None, []
         torch.cuda.set_device(self.device_index)
@@ -233,13 +235,22 @@ class PagedStack(PagedWindow):
         kind = drv.CUmemAllocationHandleType.CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR
         my_fd = -1
         try:
-            if hi > lo:
-                self._handles[rank] = _ck(drv.cuMemCreate(hi - lo, self.allocation_prop(self.device_index), 0), "cuMemCreate")
-                my_fd = int(_ck(drv.cuMemExportToShareableHandle(self._handles[rank], kind, 0), "cuMemExportToShareableHandle"))
-                self._fds.append(my_fd)
-            for owner, fd in exchange_descriptors(my_fd, self.shards, rank, group).items():
-                self._fds.append(fd)
-                self._handles[owner] = _ck(drv.cuMemImportFromShareableHandle(fd, kind), "cuMemImportFromShareableHandle")
+            if self._local:            # every rank's pages were created in this process (``on_one_device``)
+                self._handles = dict(_local_handles)
+                self._release = [rank] if rank in self._handles else []
+            else:
+                if hi > lo:
+                    self._handles[rank] = _ck(drv.cuMemCreate(hi - lo, self.allocation_prop(self.device_index), 0),
+                                              "cuMemCreate")
+                    self._release.append(rank)
+                    my_fd = int(_ck(drv.cuMemExportToShareableHandle(self._handles[rank], kind, 0),
+                                    "cuMemExportToShareableHandle"))
+                    self._fds.append(my_fd)
+                for owner, fd in exchange_descriptors(my_fd, self.shards, rank, group).items():
+                    self._fds.append(fd)
+                    self._handles[owner] = _ck(drv.cuMemImportFromShareableHandle(fd, kind),
+                                               "cuMemImportFromShareableHandle")
+                    self._release.append(owner)
             if whi > wlo:
                 self._va = int(_ck(drv.cuMemAddressReserve(whi - wlo, granularity, 0, 0), "cuMemAddressReserve"))
                 for owner, h_off, w_off, size in self.shard.maps:
@@ -275,6 +286,25 @@ class PagedStack(PagedWindow):
             raise ValueError(f"slices [{z0},{z1}) lie outside this rank's window")
         return DeviceSlab(self._va + a, (z1 - z0,) + self.frame_shape, self.dtype, self.device)
 
+    @classmethod
+    def on_one_device(cls, shards: Sequence[PagedShard], frame_shape: Tuple[int, int], dtype, device_index: int,
+                      granularity: int) -> List["PagedStack"]:
+        """Every rank's pages on ONE GPU of one process, each rank's window stitched from them: the layout, the
+        mapping calls and the kernel's reads through a stitched range, without the descriptor hand-over and without
+        NVLink (a one-GPU check of everything else)."""
+        import torch
+        from cuda.bindings import driver as drv
+
+        torch.cuda.set_device(device_index)
+        torch.empty(1, device="cuda")
+        handles = {}
+        for s in shards:
+            lo, hi = s.own_bytes
+            if hi > lo:
+                handles[s.rank] = _ck(drv.cuMemCreate(hi - lo, cls.allocation_prop(device_index), 0), "cuMemCreate")
+        return [cls(shards, s.rank, frame_shape, dtype, device_index, granularity, _local_handles=handles)
+                for s in shards]
+
     @staticmethod
     def allocation_prop(device_index: int):
         from cuda.bindings import driver as drv
@@ -303,7 +333,8 @@ class PagedStack(PagedWindow):
         import torch.distributed as dist
 
         self._torch.cuda.synchronize()
-        dist.barrier(group=self._group)
+        if not self._local:
+            dist.barrier(group=self._group)
 
     def close(self) -> None:
         drv = self._drv
@@ -311,9 +342,9 @@ class PagedStack(PagedWindow):
         for ptr, size in self._mapped:
             drv.cuMemUnmap(ptr, size)
         self._mapped = []
-        for handle in self._handles.values():
-            drv.cuMemRelease(handle)
-        self._handles = {}
+        for owner in self._release:
+            drv.cuMemRelease(self._handles[owner])
+        self._handles, self._release = {}, []
         if self._va is not None:
             wlo, whi = self.shard.window_bytes
             drv.cuMemAddressFree(self._va, whi - wlo)

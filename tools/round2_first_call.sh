@@ -15,6 +15,7 @@ run() {  # name, timeout seconds, command...
 run gpu_tests            900 python -m pytest tests -m gpu -x -q
 run aligned_rows_probe   300 python tools/probe/aligned_rows_probe.py
 run aligned_rows_test    120 env SHRIMPY_TEST_UNMEASURED=1 python -m pytest tests/test_deskew_gpu.py -q -k whole_sector
+run paged_stack_one_gpu  180 env SHRIMPY_TEST_UNMEASURED=1 python -m pytest tests/test_paged_stack_gpu.py -q -x
 run host_call_probe      300 python tools/probe/host_call_probe.py
 run bench                600 python bench.py
 tail -n 3 gpurun_out/*.out | cut -c1-400
