@@ -45,6 +45,16 @@ res = {
     "pageable_in__default_out_ms": timed(lambda: sb.deskew_data(pageable_in, *ARGS)),
     "pinned_in__default_out_ms": timed(lambda: sb.deskew_data(pinned_in, *ARGS)),
 }
+# would page-locking the caller's input for the duration of the call pay?  (register + call + unregister)
+rt = torch.cuda.cudart()
+t = time.perf_counter()
+rc = rt.cudaHostRegister(pageable_in.ctypes.data, pageable_in.nbytes, 0)
+res["host_register_737MB_ms"] = round((time.perf_counter() - t) * 1e3, 2)
+if int(rc) == 0:
+    res["registered_in__pinned_out_ms"] = timed(lambda: sb.deskew_data(pageable_in, *ARGS, out=pinned_out_t.numpy()))
+    t = time.perf_counter()
+    rt.cudaHostUnregister(pageable_in.ctypes.data)
+    res["host_unregister_ms"] = round((time.perf_counter() - t) * 1e3, 2)
 t = time.perf_counter()
 first = torch.empty((1 << 28,), dtype=torch.float32, pin_memory=True)   # 1 GiB that the cache has not seen
 res["first_pin_of_1GiB_ms"] = round((time.perf_counter() - t) * 1e3, 2)
