@@ -643,8 +643,15 @@ template <typename T>
 static int deskew_dispatch(const DeskewParams &P, int kernel, cudaStream_t stream) {
     if (kernel != SHRIMPY_KERNEL_DIRECT) {
         bool used = false;
-        const bool aligned = kernel == SHRIMPY_KERNEL_TMA_ALIGNED;
-        const int err = launch_tma<T>(P, stream, &used, kernel == SHRIMPY_KERNEL_TMA || aligned, aligned);
+        const bool forced = kernel == SHRIMPY_KERNEL_TMA_ALIGNED;
+        bool aligned = forced;
+        if (kernel == SHRIMPY_KERNEL_AUTO && !P.scale && !P.range && (P.out_s1 % 8) != 0) {
+            // Unmeasured so far, hence off unless asked for: SHRIMPY_DESKEW_ALIGNED=1 lets AUTO take the whole-sector
+            // variant for write-dominated (n == 1) deskews into rows of an odd pitch, =2 for every n.
+            static const int pref = env_int("SHRIMPY_DESKEW_ALIGNED", 0);
+            aligned = pref >= 2 || (pref == 1 && P.n == 1);
+        }
+        const int err = launch_tma<T>(P, stream, &used, kernel == SHRIMPY_KERNEL_TMA || forced, aligned);
         if (err != SHRIMPY_OK || used) return err;
     }
     return launch_direct<T>(P, stream);
