@@ -55,6 +55,19 @@ for shape, r, keep, n, dtype in [((90, 13, 128), 0.39, False, 1, torch.uint16), 
         res["equal"][key + f"_window{c0}_{c1}"] = bool(ok and bool((canvas == -7.0).all()))
     del raw, want, got, padded, canvas
 
+# every tile width the host may choose (the env is read per launch): 1, 2, 4 and 8 warps along o2
+import os
+raw = stack((120, 31, 200))
+for T2 in (32, 64, 128, 256):
+    os.environ["SHRIMPY_DESKEW_T2"] = str(T2)
+    for n in (1, 3):
+        want = sb.deskew_zyx(raw, 30.0, 0.39, True, n, kernel="tma")
+        got = torch.full_like(want, -7.0)
+        sb.deskew_zyx(raw, 30.0, 0.39, True, n, out=got, kernel="tma_aligned")
+        res["equal"][f"T2_{T2}_n{n}"] = bool(torch.equal(got, want))
+os.environ.pop("SHRIMPY_DESKEW_T2")
+del raw
+
 # ---- timings ----------------------------------------------------------------------------------------------------
 def time_it(raw, keep, n, kernel, out, reps=10):
     for _ in range(3):
