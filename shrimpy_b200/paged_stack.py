@@ -160,6 +160,31 @@ class DeviceSlab:
         return (self.shape[1] * self.shape[2], self.shape[2], 1)[axis]
 
 
+def _driver():
+    """The CUDA driver API (cuda-python).  A seam: the CPU tests substitute an emulation of the virtual-memory calls."""
+    from cuda.bindings import driver
+
+    return driver
+
+
+def _make_current(device_index: int) -> None:
+    """Make the device's primary context (torch's) current on this thread."""
+    import torch
+
+    torch.cuda.set_device(device_index)
+    torch.empty(1, device="cuda")
+
+
+def _alias_bytes(ptr: int, nbytes: int, device_index: int):
+    """uint8 tensor over ``nbytes`` of LOCAL device memory at ``ptr`` (no copy, torch does not own it)."""
+    import torch
+
+    t = torch.as_tensor(_DeviceBytes(ptr, nbytes), device=f"cuda:{device_index}")
+    if t.data_ptr() != ptr:
+        raise RuntimeError("torch copied the mapped pages instead of aliasing them")
+    return t
+
+
 def _ck(result, what: str):
     """cuda-python returns ``(CUresult, values...)``; raise on anything but success, return the values."""
     err, rest = result[0], result[1:]
@@ -214,8 +239,8 @@ class PagedStack(PagedWindow):
     def __init__(self, shards: Sequence[PagedShard], rank: int, frame_shape: Tuple[int, int], dtype, device_index: int,
                  granularity: int, group=None, _local_handles=None):
         import torch
-        from cuda.bindings import driver as drv
 
+        drv = _driver()
         self._drv, self._torch, self._group = drv, torch, group
         self.shards, self.rank, self.shard = list(shards), rank, shards[rank]
         self.frame_shape, self.dtype, self.device_index = tuple(frame_shape), dtype, int(device_index)
@@ -226,8 +251,7 @@ class PagedStack(PagedWindow):
         self._local = _local_handles is not None
         self._fds: List[int] = []
         self._va, self._mapped = None, []
-        torch.cuda.set_device(self.device_index)
-        torch.empty(1, device="cuda")                      # the primary context is current on this thread
+        _make_current(self.device_index)
         lo, hi = self.shard.own_bytes
         wlo, whi = self.shard.window_bytes
         if (hi - lo) % granularity or (whi - wlo) % granularity:
@@ -267,11 +291,12 @@ class PagedStack(PagedWindow):
         # torch only ever aliases the rank's OWN pages (local physical memory: the pointer's device is this one).  A
         # tensor over the whole window would start in a neighbour's pages, torch would attribute it to that GPU and
         # ``device=`` would then mean a copy; the window is handed to the kernels as a raw address (``DeviceSlab``).
-        self.own = (torch.as_tensor(_DeviceBytes(self._va + (lo - wlo), hi - lo), device=f"cuda:{self.device_index}")
-                    if hi > lo else torch.empty(0, dtype=torch.uint8, device=f"cuda:{self.device_index}"))
-        if hi > lo and self.own.data_ptr() != self._va + (lo - wlo):
+        try:
+            self.own = (_alias_bytes(self._va + (lo - wlo), hi - lo, self.device_index) if hi > lo
+                        else torch.empty(0, dtype=torch.uint8))
+        except BaseException:
             self.close()
-            raise RuntimeError("torch copied the mapped pages instead of aliasing them")
+            raise
 
     @property
     def device(self):
@@ -292,11 +317,8 @@ class PagedStack(PagedWindow):
         """Every rank's pages on ONE GPU of one process, each rank's window stitched from them: the layout, the
         mapping calls and the kernel's reads through a stitched range, without the descriptor hand-over and without
         NVLink (a one-GPU check of everything else)."""
-        import torch
-        from cuda.bindings import driver as drv
-
-        torch.cuda.set_device(device_index)
-        torch.empty(1, device="cuda")
+        drv = _driver()
+        _make_current(device_index)
         handles = {}
         for s in shards:
             lo, hi = s.own_bytes
@@ -307,7 +329,7 @@ class PagedStack(PagedWindow):
 
     @staticmethod
     def allocation_prop(device_index: int):
-        from cuda.bindings import driver as drv
+        drv = _driver()
 
         prop = drv.CUmemAllocationProp()
         prop.type = drv.CUmemAllocationType.CU_MEM_ALLOCATION_TYPE_PINNED
@@ -319,11 +341,8 @@ class PagedStack(PagedWindow):
     @staticmethod
     def granularity(device_index: int) -> int:
         """Allocation granularity of exportable device memory on this GPU (the page size of the plan)."""
-        import torch
-        from cuda.bindings import driver as drv
-
-        torch.cuda.set_device(device_index)
-        torch.empty(1, device="cuda")
+        drv = _driver()
+        _make_current(device_index)
         flag = drv.CUmemAllocationGranularity_flags.CU_MEM_ALLOC_GRANULARITY_RECOMMENDED
         return int(_ck(drv.cuMemGetAllocationGranularity(PagedStack.allocation_prop(device_index), flag),
                        "cuMemGetAllocationGranularity"))

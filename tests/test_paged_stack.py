@@ -152,3 +152,112 @@ def test_device_slab_describes_a_contiguous_stack_like_a_tensor():
     like = torch.empty((5, 13, 8), dtype=torch.uint16)
     assert slab.shape == tuple(like.shape) and slab.dtype == like.dtype
     assert [slab.stride(i) for i in range(3)] == list(like.stride()) and slab.data_ptr() == 0x7f0000000000
+
+
+class EmulatedDriver:
+    """The virtual-memory calls ``PagedStack`` makes, emulated on host bytes: physical handles are numpy arrays, a
+    reserved range is a number, ``cuMemMap`` records which bytes of which handle answer at which address.  Enums and
+    structs are cuda-python's own (they import without a driver), so a misspelt field fails here as it would there."""
+
+    def __init__(self):
+        from cuda.bindings import driver
+
+        self._real = driver
+        self.storage, self.mappings, self.reserved, self.access, self.released = {}, [], {}, [], []
+        self._next_handle, self._next_va = 1, 0x7F0000000000
+
+    def __getattr__(self, name):
+        return getattr(self._real, name)
+
+    def cuMemGetAllocationGranularity(self, prop, option):
+        assert prop.requestedHandleTypes == self._real.CUmemAllocationHandleType.CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR
+        return (self._real.CUresult.CUDA_SUCCESS, 4096)
+
+    def cuMemCreate(self, size, prop, flags):
+        assert size > 0 and size % 4096 == 0 and flags == 0
+        assert prop.location.type == self._real.CUmemLocationType.CU_MEM_LOCATION_TYPE_DEVICE
+        handle, self._next_handle = self._next_handle, self._next_handle + 1
+        self.storage[handle] = np.zeros(size, dtype=np.uint8)
+        return (self._real.CUresult.CUDA_SUCCESS, handle)
+
+    def cuMemAddressReserve(self, size, alignment, addr, flags):
+        va, self._next_va = self._next_va, self._next_va + size + (1 << 30)
+        self.reserved[va] = size
+        return (self._real.CUresult.CUDA_SUCCESS, self._real.CUdeviceptr(va))
+
+    def cuMemMap(self, ptr, size, offset, handle, flags):
+        base = max(v for v in self.reserved if v <= ptr)
+        assert ptr + size <= base + self.reserved[base], "mapping outside the reserved range"
+        assert offset % 4096 == 0 and size % 4096 == 0 and offset + size <= self.storage[handle].size
+        assert all(ptr + size <= p or p + n <= ptr for p, n, _, _ in self.mappings), "address mapped twice"
+        self.mappings.append((ptr, size, handle, offset))
+        return (self._real.CUresult.CUDA_SUCCESS,)
+
+    def cuMemSetAccess(self, ptr, size, desc, count):
+        assert count == 1 and desc[0].flags == self._real.CUmemAccess_flags.CU_MEM_ACCESS_FLAGS_PROT_READWRITE
+        self.access.append((ptr, size, desc[0].location.id))
+        return (self._real.CUresult.CUDA_SUCCESS,)
+
+    def cuMemUnmap(self, ptr, size):
+        self.mappings = [m for m in self.mappings if not (m[0] == ptr and m[1] == size)]
+        return (self._real.CUresult.CUDA_SUCCESS,)
+
+    def cuMemRelease(self, handle):
+        self.released.append(handle)
+        return (self._real.CUresult.CUDA_SUCCESS,)
+
+    def cuMemAddressFree(self, ptr, size):
+        assert self.reserved.pop(ptr) == size
+        return (self._real.CUresult.CUDA_SUCCESS,)
+
+    # what the hardware does with the mappings
+    def view(self, ptr, nbytes):
+        for p, n, handle, offset in self.mappings:
+            if p <= ptr and ptr + nbytes <= p + n:
+                return self.storage[handle][offset + ptr - p:offset + ptr - p + nbytes]
+        raise AssertionError("range is not inside one mapping")
+
+    def read(self, ptr, nbytes):
+        out = np.empty(nbytes, dtype=np.uint8)
+        done = 0
+        while done < nbytes:
+            p, n, handle, offset = next(m for m in self.mappings if m[0] <= ptr + done < m[0] + m[1])
+            take = min(nbytes - done, p + n - (ptr + done))
+            out[done:done + take] = self.storage[handle][offset + ptr + done - p:offset + ptr + done - p + take]
+            done += take
+        return out
+
+
+@pytest.mark.parametrize("world,keep,n", [(1, True, 1), (3, True, 1), (4, False, 3)])
+def test_paged_stack_call_sequence_on_an_emulated_driver(monkeypatch, world, keep, n):
+    """``PagedStack.on_one_device`` end to end with the driver emulated: the addresses ``slices`` hands to the kernel
+    resolve, through the recorded mappings, to exactly the raw slices; everything is unmapped and released on close."""
+    drv = EmulatedDriver()
+    monkeypatch.setattr(ps, "_driver", lambda: drv)
+    monkeypatch.setattr(ps, "_make_current", lambda device_index: None)
+    monkeypatch.setattr(ps, "_alias_bytes", lambda ptr, nbytes, device_index: torch.from_numpy(drv.view(ptr, nbytes)))
+    shape = (260, 12, 64)                                   # 1536-byte slices, 4096-byte pages
+    raw = synthetic_stack(shape, seed=33)
+    g = sb.deskew_geometry(shape, 30.0, 0.39, keep, n)
+    page = ps.PagedStack.granularity(0)
+    shards = ps.plan_paged_split(g, world, shape[1] * shape[2] * 2, page, align=8)
+    stacks = ps.PagedStack.on_one_device(shards, shape[1:], torch.uint16, 0, page)
+    for st in stacks:
+        st.fill_own(lambda z0, z1: torch.from_numpy(raw[z0:z1].copy()))
+    assert sorted(a[0] for a in drv.access) == sorted(st._va for st in stacks)
+
+    def window_through_the_mappings(slab, g, p_begin, p_count, c_begin, c_count, y_origin, z_origin, cval):
+        assert isinstance(slab, ps.DeviceSlab)
+        data = drv.read(slab.data_ptr(), int(np.prod(slab.shape)) * 2).view(np.uint16).reshape(slab.shape)
+        assert np.array_equal(data, raw[z_origin:z_origin + slab.shape[0]])
+        return numpy_window(torch.from_numpy(data), g, p_begin, p_count, c_begin, c_count, y_origin, z_origin, cval)
+
+    pieces = [ps.deskew_paged_split(st, g, st.shard, cval=-3.0, window_fn=window_through_the_mappings).numpy()
+              for st in stacks if st.shard.need_z[1] > st.shard.need_z[0]]
+    whole = o.deskew_data(raw, 30.0, 0.39, keep, n, cval=-3.0)
+    got = np.concatenate(pieces, axis=2)
+    assert got.shape == whole.shape and np.array_equal(got == -3.0, whole == -3.0)
+    assert np.max(np.abs(got - whole)) <= 2e-6 * float(whole.max() - whole.min())
+    for st in stacks:
+        st.close()
+    assert not drv.mappings and not drv.reserved and sorted(drv.released) == sorted(drv.storage)
