@@ -16,8 +16,8 @@ multiples of the allocation granularity (2 MiB), and a mantis slice (300 x 2048 
 slice that straddles a page boundary simply has its head on one GPU and its tail on the next.
 
 Status: the layout arithmetic and the descriptor exchange are covered by CPU tests (``tests/test_paged_stack.py``:
-every byte a rank's columns read is mapped, stitched windows equal the stack, 2-process fd hand-over over unix
-sockets).  The driver calls were written after round 1's GPU minutes ran out and have NOT run on a GPU yet:
+every byte a rank's columns read is mapped, stitched windows equal the stack, 3-process fd hand-over over unix
+sockets, the whole call sequence against an emulation of the driver's virtual-memory calls).  The driver calls were written after round 1's GPU minutes ran out and have NOT run on a GPU yet:
 ``tools/scan_split_bench.py --transport vmm`` is the first thing to run (2 GPUs) before anything relies on it.
 """
 
