@@ -35,6 +35,13 @@ container (scipy 1.18.1): coordinates are accumulated in float64 as
 ``((shift + o0*M00) + o1*M01) + o2*M02`` with no fused multiply-add, and the
 ``mode="constant"`` inside test is strict (``0 <= c <= len-1``, no tolerance).
 
+Scope: FINITE raw voxels (camera stacks are uint16).  With a NaN or infinite float32 voxel the statements stop
+agreeing, by construction: scipy multiplies all eight trilinear taps, zero weights included, so the voxel poisons
+outputs whose zero-weight y/x taps touch it (``0 * nan``), while the closed form here, the C restatement and the CUDA
+kernels interpolate along scan only; and the kernels evaluate ``a + w (b - a)`` where scipy evaluates
+``(1 - w) a + w b``, so an infinite tap becomes NaN there and stays infinite here
+(``tests/test_oracle.py::test_non_finite_voxels_are_outside_the_parity_contract``).
+
 Open ambiguities that cannot be resolved offline (recorded, not hidden):
 default ``cval`` (scipy generation used ``min(raw)``, the torch/monai
 generation pads with zeros -- the oracle takes ``cval`` explicitly, default
