@@ -69,11 +69,20 @@ const char *shrimpy_last_error(void);
  *   row0[3]       = (M00, M02, Z_shift) of the output->input affine row that
  *                   maps (o0, o2) to the scan coordinate:
  *                   z_in = (Z_shift + o0*M00) + o2*M02
- * All arithmetic in float64, libm cos/sin.
+ * All arithmetic in float64, libm cos/sin of theta = ls_angle_deg * pi / 180.
+ *
+ * shrimpy_deskew_geometry_trig is the same computation with cos(theta) and sin(theta) supplied by the caller.  It is
+ * the ONE code path of the geometry: the Python host calls it with numpy's cos / sin (what the upstream Python
+ * evaluates), shrimpy_deskew_geometry calls it with libm's.  numpy and libm may differ in the last bit of a cosine,
+ * and one ulp in M00 can move a voxel across the strict inside/outside rule or change ceil() in Xp; a host that must
+ * reproduce the Python path bit for bit passes the trig values the Python path used.
  */
 int shrimpy_deskew_geometry(int Z, int Y, int X, double ls_angle_deg, double px_to_scan_ratio,
                             int keep_overhang, int average_n_slices, double pixel_size_um,
                             int64_t out_shape[3], double voxel_size[3], double row0[3]);
+int shrimpy_deskew_geometry_trig(int Z, int Y, int X, double cos_theta, double sin_theta, double px_to_scan_ratio,
+                                 int keep_overhang, int average_n_slices, double pixel_size_um,
+                                 int64_t out_shape[3], double voxel_size[3], double row0[3]);
 
 /*
  * Device-resident deskew of one stack (replaces the body of
@@ -200,9 +209,15 @@ int shrimpy_min_device(const void *d_raw, int raw_dtype, int64_t count, float *d
  * scripts/measure_psf.py:239-246: numpy in, numpy out).  The stack is cut into
  * tilt slabs (multiples of n_avg rows, halo-free: SURVEY.md 8e) that are
  * streamed H2D -> kernel -> D2H on three streams with double-buffered device
- * slabs.  h_raw / h_out may be pageable; pinned (cudaHostRegister'd or
- * cudaHostAlloc'd) buffers make the copies truly asynchronous.
- * Synchronous: returns when h_out is complete.
+ * slabs.  h_raw / h_out may be pageable (an ordinary numpy array, as
+ * scripts/measure_psf.py:239-246 passes): such a buffer is gathered into /
+ * scattered out of a page-locked ring by a few host threads
+ * (SHRIMPY_HOST_THREADS, default min(8, cores/2)) while the neighbouring slabs'
+ * copies and kernels run, so the GPU only ever sees asynchronous page-locked
+ * transfers; pinned buffers are copied directly.
+ * Synchronous: returns when h_out is complete, and with nothing in flight
+ * whatever it returns.  Calls on one pipeline are serialised by a mutex inside
+ * it; distinct pipelines run concurrently.
  */
 typedef struct shrimpy_pipeline shrimpy_pipeline;
 
@@ -212,6 +227,8 @@ int shrimpy_deskew_host(shrimpy_pipeline *p, const void *h_raw, int raw_dtype, f
                         int X, int Xp, int n_avg, double m00, double m02, double shift, float cval);
 /* counters of the last shrimpy_deskew_host call: kernels launched, H2D / D2H bytes */
 int shrimpy_pipeline_stats(const shrimpy_pipeline *p, int64_t *launches, int64_t *h2d_bytes, int64_t *d2h_bytes);
+/* bytes of the last call that went through the pipeline's own page-locked staging rings (pageable h_raw / h_out) */
+int shrimpy_pipeline_staged_bytes(const shrimpy_pipeline *p, int64_t *in_bytes, int64_t *out_bytes);
 
 /*
  * Blosc-1 frame codec for the OME-Zarr chunk loader (host memory only; no CUDA call).  The reference acquires with

@@ -24,6 +24,7 @@ EXPORTS = (
     "shrimpy_abi_version",
     "shrimpy_last_error",
     "shrimpy_deskew_geometry",
+    "shrimpy_deskew_geometry_trig",
     "shrimpy_deskew_device",
     "shrimpy_deskew_window_needs",
     "shrimpy_deskew_window_device",
@@ -43,6 +44,7 @@ EXPORTS = (
     "shrimpy_pipeline_destroy",
     "shrimpy_deskew_host",
     "shrimpy_pipeline_stats",
+    "shrimpy_pipeline_staged_bytes",
     "shrimpy_blosc_info",
     "shrimpy_blosc_decode",
     "shrimpy_blosc_encode_bound",
@@ -84,6 +86,9 @@ def _declare(lib) -> None:
     lib.shrimpy_deskew_geometry.restype = c_int
     lib.shrimpy_deskew_geometry.argtypes = [c_int, c_int, c_int, c_dbl, c_dbl, c_int, c_int, c_dbl,
                                             ctypes.POINTER(c_i64), ctypes.POINTER(c_dbl), ctypes.POINTER(c_dbl)]
+    lib.shrimpy_deskew_geometry_trig.restype = c_int
+    lib.shrimpy_deskew_geometry_trig.argtypes = [c_int, c_int, c_int, c_dbl, c_dbl, c_dbl, c_int, c_int, c_dbl,
+                                                 ctypes.POINTER(c_i64), ctypes.POINTER(c_dbl), ctypes.POINTER(c_dbl)]
     deskew_common = [c_vp, c_int, c_vp, c_int, c_int, c_int, c_int, c_int, c_dbl, c_dbl, c_dbl, c_flt,
                      c_i64, c_i64, c_i64, c_i64]
     lib.shrimpy_deskew_device.restype = c_int
@@ -131,6 +136,8 @@ def _declare(lib) -> None:
                                         c_dbl, c_dbl, c_dbl, c_flt]
     lib.shrimpy_pipeline_stats.restype = c_int
     lib.shrimpy_pipeline_stats.argtypes = [c_vp, ctypes.POINTER(c_i64), ctypes.POINTER(c_i64), ctypes.POINTER(c_i64)]
+    lib.shrimpy_pipeline_staged_bytes.restype = c_int
+    lib.shrimpy_pipeline_staged_bytes.argtypes = [c_vp, ctypes.POINTER(c_i64), ctypes.POINTER(c_i64)]
     c_sz, c_i32 = ctypes.c_size_t, ctypes.c_int32
     lib.shrimpy_blosc_info.restype = c_int
     lib.shrimpy_blosc_info.argtypes = [c_vp, c_sz, ctypes.POINTER(c_i64), ctypes.POINTER(c_i64), ctypes.POINTER(c_i32),

@@ -222,7 +222,14 @@ int parse(const uint8_t *src, size_t srclen, Frame &f) {
                     f.cbytes, srclen);
     if (f.typesize < 1) return fail(SHRIMPY_EINVAL, "blosc: typesize 0");
     if (f.nbytes > 0 && f.blocksize <= 0) return fail(SHRIMPY_EINVAL, "blosc: blocksize %d", f.blocksize);
-    f.nblocks = f.nbytes == 0 ? 0 : (f.nbytes + f.blocksize - 1) / f.blocksize;
+    // untrusted header fields: all size arithmetic in 64 bits.  c-blosc never writes a block larger than the
+    // buffer (blocksize is clamped to nbytes), so a larger one is a corrupt header, not a layout to interpret.
+    if (f.nbytes > 0 && f.blocksize > f.nbytes)
+        return fail(SHRIMPY_EINVAL, "blosc: blocksize %d exceeds the frame's %d bytes", f.blocksize, f.nbytes);
+    const int64_t nblocks = f.nbytes == 0 ? 0 : ((int64_t)f.nbytes + f.blocksize - 1) / f.blocksize;
+    if (f.nbytes > 0 && (nblocks <= 0 || nblocks > INT32_MAX / 4))
+        return fail(SHRIMPY_EINVAL, "blosc: %lld blocks", (long long)nblocks);
+    f.nblocks = (int32_t)nblocks;
     return SHRIMPY_OK;
 }
 
@@ -236,7 +243,7 @@ inline int splits_of(const Frame &f, int32_t bsize, bool leftover) {
 // decode block b; tmp holds >= blocksize bytes. Returns 0 or an error code (message set).
 int decode_block(const Frame &f, const uint8_t *src, int32_t b, uint8_t *dst, uint8_t *tmp) {
     const bool last = b == f.nblocks - 1;
-    const int32_t bsize = last ? f.nbytes - b * f.blocksize : f.blocksize;
+    const int32_t bsize = last ? (int32_t)((int64_t)f.nbytes - (int64_t)b * f.blocksize) : f.blocksize;
     const bool leftover = last && bsize != f.blocksize;
     const bool shuf = (f.flags & F_SHUFFLE) && f.typesize > 1;
     const bool bshuf = !shuf && (f.flags & F_BITSHUFFLE) && bsize >= f.typesize;
@@ -251,7 +258,7 @@ int decode_block(const Frame &f, const uint8_t *src, int32_t b, uint8_t *dst, ui
         if (pos + 4 > f.cbytes) return fail(SHRIMPY_EINVAL, "blosc: block %d is truncated", b);
         const int32_t csize = rd32(src + pos);
         pos += 4;
-        if (csize < 0 || pos + csize > f.cbytes) return fail(SHRIMPY_EINVAL, "blosc: stream %d of block %d is truncated", j, b);
+        if (csize < 0 || pos + (int64_t)csize > (int64_t)f.cbytes) return fail(SHRIMPY_EINVAL, "blosc: stream %d of block %d is truncated", j, b);
         if (csize == neblock)
             memcpy(work, src + pos, (size_t)neblock);
         else if (!inflate(f.codec, src + pos, csize, work, neblock))
@@ -291,7 +298,7 @@ extern "C" int shrimpy_blosc_decode(const void *frame, size_t frame_bytes, void 
     if (f.nbytes == 0) return SHRIMPY_OK;
     if (!dst) return fail(SHRIMPY_EINVAL, "blosc: null destination");
     if (f.flags & F_MEMCPY) {
-        if (f.cbytes < kHeader + f.nbytes) return fail(SHRIMPY_EINVAL, "blosc: stored frame is truncated");
+        if ((int64_t)f.cbytes < (int64_t)kHeader + (int64_t)f.nbytes) return fail(SHRIMPY_EINVAL, "blosc: stored frame is truncated");
         memcpy(dst, src + kHeader, (size_t)f.nbytes);
         return SHRIMPY_OK;
     }

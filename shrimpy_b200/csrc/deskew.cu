@@ -646,9 +646,11 @@ static int deskew_dispatch(const DeskewParams &P, int kernel, cudaStream_t strea
         const bool forced = kernel == SHRIMPY_KERNEL_TMA_ALIGNED;
         bool aligned = forced;
         if (kernel == SHRIMPY_KERNEL_AUTO && !P.scale && !P.range && (P.out_s1 % 8) != 0) {
-            // Unmeasured so far, hence off unless asked for: SHRIMPY_DESKEW_ALIGNED=1 lets AUTO take the whole-sector
-            // variant for write-dominated (n == 1) deskews into rows of an odd pitch, =2 for every n.
-            static const int pref = env_int("SHRIMPY_DESKEW_ALIGNED", 0);
+            // Measured on B200 (profiles/r02_aligned_rows_probe.json): into rows of an odd pitch the whole-sector
+            // variant wins where the writes dominate -- n = 1: 0.829 -> 0.780 ms, keep_overhang 1.197 -> 1.114 ms,
+            // config 5 7.17 -> 6.85 ms -- and loses 14-18 % for n >= 2 (a sixth tile per 1279-column row costs more than
+            // the partial sectors).  AUTO therefore takes it for n == 1 only; SHRIMPY_DESKEW_ALIGNED=0 / 2 = never / always.
+            static const int pref = env_int("SHRIMPY_DESKEW_ALIGNED", 1);
             aligned = pref >= 2 || (pref == 1 && P.n == 1);
         }
         const int err = launch_tma<T>(P, stream, &used, kernel == SHRIMPY_KERNEL_TMA || forced, aligned);

@@ -80,13 +80,17 @@ extern "C" const char *shrimpy_last_error(void) { return last_error_buffer(); }
 
 extern "C" int64_t shrimpy_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
-extern "C" int shrimpy_deskew_geometry(int Z, int Y, int X, double ls_angle_deg, double px_to_scan_ratio,
-                                       int keep_overhang, int average_n_slices, double pixel_size_um,
-                                       int64_t out_shape[3], double voxel_size[3], double row0[3]) {
+// The one place the scalar geometry is computed: the Python host (shrimpy_b200/deskew.py) calls it with numpy's
+// cos / sin -- what the upstream Python evaluates -- and shrimpy_deskew_geometry with libm's.  Every product and sum
+// is rounded separately (volatile temporaries, -ffp-contract=off), in the order the upstream expressions have.
+extern "C" int shrimpy_deskew_geometry_trig(int Z, int Y, int X, double cos_theta, double sin_theta,
+                                            double px_to_scan_ratio, int keep_overhang, int average_n_slices,
+                                            double pixel_size_um, int64_t out_shape[3], double voxel_size[3],
+                                            double row0[3]) {
     if (Z <= 0 || Y <= 0 || X <= 0 || average_n_slices <= 0 || !(px_to_scan_ratio > 0.0))
         return fail(SHRIMPY_EINVAL, "geometry: bad arguments");
-    const double theta = ls_angle_deg * M_PI / 180.0;
-    const double st = sin(theta), ct = cos(theta);
+    if (!std::isfinite(cos_theta) || !std::isfinite(sin_theta)) return fail(SHRIMPY_EINVAL, "geometry: non-finite angle");
+    const double st = sin_theta, ct = cos_theta;
     volatile double zr = (double)Z / px_to_scan_ratio;
     volatile double yc = (double)Y * ct;
     const double xp = keep_overhang ? ceil(zr + yc) : ceil(zr - yc);
@@ -96,7 +100,8 @@ extern "C" int shrimpy_deskew_geometry(int Z, int Y, int X, double ls_angle_deg,
         out_shape[2] = xp > 0.0 ? (int64_t)xp : 0;
     }
     if (voxel_size) {
-        voxel_size[0] = (double)average_n_slices * st * pixel_size_um;
+        volatile double nst = (double)average_n_slices * st;
+        voxel_size[0] = nst * pixel_size_um;
         voxel_size[1] = pixel_size_um;
         voxel_size[2] = pixel_size_um;
     }
@@ -107,6 +112,15 @@ extern "C" int shrimpy_deskew_geometry(int Z, int Y, int X, double ls_angle_deg,
         row0[2] = keep_overhang ? 0.0 : floor(yct * px_to_scan_ratio);
     }
     return SHRIMPY_OK;
+}
+
+extern "C" int shrimpy_deskew_geometry(int Z, int Y, int X, double ls_angle_deg, double px_to_scan_ratio,
+                                       int keep_overhang, int average_n_slices, double pixel_size_um,
+                                       int64_t out_shape[3], double voxel_size[3], double row0[3]) {
+    volatile double deg_pi = ls_angle_deg * M_PI;
+    const double theta = deg_pi / 180.0;
+    return shrimpy_deskew_geometry_trig(Z, Y, X, cos(theta), sin(theta), px_to_scan_ratio, keep_overhang,
+                                        average_n_slices, pixel_size_um, out_shape, voxel_size, row0);
 }
 
 extern "C" int shrimpy_min_device(const void *d_raw, int raw_dtype, int64_t count, float *d_result, void *stream) {

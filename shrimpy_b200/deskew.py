@@ -20,6 +20,7 @@ from __future__ import annotations
 
 import ctypes
 import math
+import threading
 from dataclasses import dataclass
 from typing import Optional, Sequence, Tuple, Union
 
@@ -86,21 +87,18 @@ def deskew_geometry(raw_data_shape: Sequence[int], ls_angle_deg: float, px_to_sc
         raise ValueError(f"non-positive size in raw_data_shape={tuple(raw_data_shape)} / average_n_slices={n}")
     if not px_to_scan_ratio > 0:
         raise ValueError("px_to_scan_ratio must be positive")
+    # numpy's cos / sin, as the upstream Python evaluates them; everything after that is the C-ABI's one geometry
+    # routine, so a C host that passes the same two numbers gets this geometry bit for bit (include/shrimpy_b200.h)
     theta = ls_angle_deg * np.pi / 180
-    sin_t, cos_t = np.sin(theta), np.cos(theta)
-    overhang = Y * cos_t
-    extent = Z / px_to_scan_ratio
-    Xp = int(np.ceil(extent + overhang)) if keep_overhang else int(np.ceil(extent - overhang))
-    shift = 0 if keep_overhang else int(np.floor(Y * cos_t * px_to_scan_ratio))
-    return DeskewGeometry(
-        raw_shape=(Z, Y, X),
-        out_shape=(-(-Y // n), X, max(Xp, 0)),
-        voxel_size=(n * sin_t * pixel_size_um, pixel_size_um, pixel_size_um),
-        n_avg=n,
-        m00=float(-px_to_scan_ratio * cos_t),
-        m02=float(px_to_scan_ratio),
-        shift=float(shift),
-    )
+    shape = (ctypes.c_int64 * 3)()
+    vox = (ctypes.c_double * 3)()
+    row = (ctypes.c_double * 3)()
+    _cabi.check(_cabi.lib().shrimpy_deskew_geometry_trig(
+        Z, Y, X, float(np.cos(theta)), float(np.sin(theta)), float(px_to_scan_ratio), int(bool(keep_overhang)), n,
+        float(pixel_size_um), shape, vox, row))
+    voxel_size = (float(vox[0]), pixel_size_um, pixel_size_um)     # the caller's own objects for the two plain copies
+    return DeskewGeometry(raw_shape=(Z, Y, X), out_shape=(int(shape[0]), int(shape[1]), int(shape[2])),
+                          voxel_size=voxel_size, n_avg=n, m00=float(row[0]), m02=float(row[1]), shift=float(row[2]))
 
 
 def get_deskewed_data_shape(raw_data_shape: Sequence[int], ls_angle_deg: float, px_to_scan_ratio: float,
@@ -145,10 +143,41 @@ def _device_dtype(torch, t):
 def _resolve_cval(torch, raw, code, cval, stream) -> float:
     if cval is not None:
         return float(cval)
-    # scipy-generation default: pad with min(raw); reduced on the device
+    # scipy-generation default: pad with min(raw); reduced on the device.  The reduction walks `numel` consecutive
+    # elements, so a strided view (an X chunk, a row-padded stack) is compacted first: its minimum is over the view's
+    # own voxels, like `raw.min()` in deskew_data.
+    dense = raw if raw.is_contiguous() else raw.contiguous()
     slot = torch.empty(1, dtype=torch.float32, device=raw.device)
-    _cabi.check(_cabi.lib().shrimpy_min_device(raw.data_ptr(), code, raw.numel(), slot.data_ptr(), stream))
+    _cabi.check(_cabi.lib().shrimpy_min_device(dense.data_ptr(), code, dense.numel(), slot.data_ptr(), stream))
     return float(slot.item())
+
+
+def _kernel_view(raw):
+    """``raw`` in a layout the kernels address -- unit stride along x, rows and slices that do not overlap -- without a
+    copy when it already is (C-contiguous stacks, X-chunk views, padded rows), compacted otherwise (transposed views,
+    and broadcast views such as ``plane[None].expand(Z, Y, X)`` whose zero strides the C-ABI would read as "use the
+    contiguous default").  Returns ``(tensor, stride_z, stride_y)`` in elements, never 0."""
+    Z, Y, X = raw.shape
+    sz, sy, sx = raw.stride()
+    ok = raw.numel() > 0 and (sx == 1 or X == 1) and (Y == 1 or sy >= X) and (Z == 1 or sz >= (Y - 1) * (sy if Y > 1 else 0) + X)
+    if not ok:
+        raw = raw.contiguous()
+        return raw, Y * X, X
+    sy = sy if Y > 1 else X
+    sz = sz if Z > 1 else Y * sy
+    return raw, sz, sy
+
+
+def _check_out(torch, out, shape, device, what="out"):
+    P, X, C = shape
+    if (tuple(out.shape) != tuple(shape) or out.dtype != torch.float32 or out.device != device
+            or (out.numel() and ((C > 1 and out.stride(2) != 1) or (X > 1 and out.stride(1) < C)
+                                 or (P > 1 and out.stride(0) < (X - 1) * (out.stride(1) if X > 1 else 0) + C)))):
+        raise ValueError(f"{what} must be a float32 tensor of shape {tuple(shape)} on {device} with unit stride along "
+                         "the last axis and non-overlapping rows and planes (see empty_deskewed)")
+    s1 = out.stride(1) if X > 1 else C
+    s0 = out.stride(0) if P > 1 else X * s1
+    return s0, s1
 
 
 def deskew_zyx(raw_data, ls_angle_deg: float, px_to_scan_ratio: float, keep_overhang: bool,
@@ -170,17 +199,12 @@ def deskew_zyx(raw_data, ls_angle_deg: float, px_to_scan_ratio: float, keep_over
         raise RuntimeError("deskew_zyx expects a CUDA tensor")
     g = deskew_geometry(tuple(raw_data.shape), ls_angle_deg, px_to_scan_ratio, keep_overhang, average_n_slices)
     code, raw = _device_dtype(torch, raw_data)
-    if raw.stride(2) != 1 or raw.numel() == 0:
-        raw = raw.contiguous()
+    raw, raw_sz, raw_sy = _kernel_view(raw)
     with torch.cuda.device(raw.device):
         stream = torch.cuda.current_stream().cuda_stream
         if out is None:
             out = torch.empty(g.out_shape, dtype=torch.float32, device=raw.device)
-        elif (tuple(out.shape) != g.out_shape or out.dtype != torch.float32 or out.device != raw.device
-              or (out.numel() and (out.stride(2) != 1 or out.stride(1) < g.out_shape[2]
-                                   or out.stride(0) < g.out_shape[1] * out.stride(1)))):
-            raise ValueError(f"out must be a float32 tensor of shape {g.out_shape} on {raw.device} with unit stride along "
-                             "the last axis and non-overlapping rows and planes (see empty_deskewed)")
+        out_s0, out_s1 = _check_out(torch, out, g.out_shape, raw.device)
         if out.numel() == 0:
             return out
         if not out.is_contiguous() and (value_range is not None or scale is not None):
@@ -197,13 +221,13 @@ def deskew_zyx(raw_data, ls_angle_deg: float, px_to_scan_ratio: float, keep_over
             _cabi.check(_cabi.lib().shrimpy_deskew_range_device(
                 raw.data_ptr(), code, scale.data_ptr() if scale is not None else None, out.data_ptr(),
                 value_range.data_ptr(), Z, Y, X, g.out_shape[2], g.n_avg, g.m00, g.m02, g.shift, fill,
-                raw.stride(0), raw.stride(1), _cabi.KERNELS[kernel], stream))
+                raw_sz, raw_sy, _cabi.KERNELS[kernel], stream))
             return out
         if scale is not None:
             raise ValueError("scale is only taken together with value_range; use flatfield.deskew_flat_field_zyx")
         _cabi.check(_cabi.lib().shrimpy_deskew_device(
             raw.data_ptr(), code, out.data_ptr(), Z, Y, X, g.out_shape[2], g.n_avg, g.m00, g.m02, g.shift, fill,
-            raw.stride(0), raw.stride(1), out.stride(0), out.stride(1), _cabi.KERNELS[kernel], stream))
+            raw_sz, raw_sy, out_s0, out_s1, _cabi.KERNELS[kernel], stream))
     return out
 
 
@@ -265,9 +289,12 @@ def deskew_window(raw_slab, g: DeskewGeometry, *, p_begin: int, p_count: int, c_
     geometry ``g`` is that of the FULL stack so the voxels equal the un-windowed result bit for bit.
     """
     torch = _torch()
+    is_tensor = isinstance(raw_slab, torch.Tensor)     # paged_stack.DeviceSlab: an address and a shape, always dense
     code, raw = _device_dtype(torch, raw_slab)
-    if raw.stride(2) != 1:
-        raw = raw.contiguous()
+    if is_tensor:
+        raw, raw_sz, raw_sy = _kernel_view(raw)
+    else:
+        raw_sz, raw_sy = raw.stride(0), raw.stride(1)
     Z, Y, X = g.raw_shape
     if raw.shape[2] != X:
         raise ValueError("slab must span the full raw X axis")
@@ -275,10 +302,13 @@ def deskew_window(raw_slab, g: DeskewGeometry, *, p_begin: int, p_count: int, c_
         stream = torch.cuda.current_stream().cuda_stream
         if out is None:
             out = torch.empty((p_count, X, c_count), dtype=torch.float32, device=raw.device)
+        out_s0, out_s1 = _check_out(torch, out, (p_count, X, c_count), raw.device)
+        if out.numel() == 0:
+            return out
         win = _cabi.Window(p_begin, p_count, c_begin, c_count, y_origin, raw.shape[1], z_origin, raw.shape[0])
         _cabi.check(_cabi.lib().shrimpy_deskew_window_device(
             raw.data_ptr(), code, out.data_ptr(), Z, Y, X, g.out_shape[2], g.n_avg, g.m00, g.m02, g.shift,
-            float(cval), raw.stride(0), raw.stride(1), out.stride(0), out.stride(1), ctypes.byref(win),
+            float(cval), raw_sz, raw_sy, out_s0, out_s1, ctypes.byref(win),
             _cabi.KERNELS[kernel], stream))
     return out
 
@@ -341,12 +371,21 @@ class HostPipeline:
 
 
 _pipelines: dict = {}
+_pipelines_lock = threading.Lock()
 
 
 def _pipeline_for(index: int) -> HostPipeline:
-    pipe = _pipelines.get(index)
-    if pipe is None:
-        pipe = _pipelines[index] = HostPipeline(index)
+    """One pipeline per (device, calling thread): two threads that call ``deskew_data`` on the same GPU (an IO pool
+    over positions) each stream through their own slots and streams and overlap; a pipeline that is nevertheless
+    shared is serialised by the mutex inside it (``csrc/pipeline.cu``)."""
+    key = (index, threading.get_ident())
+    with _pipelines_lock:
+        pipe = _pipelines.get(key)
+        if pipe is None:
+            dead = {t.ident for t in threading.enumerate()}
+            for k in [k for k in _pipelines if k[1] not in dead]:      # threads that have ended: free their device slabs
+                _pipelines.pop(k).close()
+            pipe = _pipelines[key] = HostPipeline(index)
     return pipe
 
 

@@ -18,7 +18,7 @@ import ctypes
 from typing import Optional
 
 from . import _cabi
-from .deskew import _device_dtype, deskew_geometry
+from .deskew import _device_dtype, _kernel_view, deskew_geometry
 
 __all__ = ["flat_field_pattern", "flat_field_scale", "flat_field_BF", "deskew_flat_field_zyx"]
 
@@ -31,24 +31,25 @@ def _prep(volume):
     if volume.dim() != 3:
         raise ValueError(f"volume must be (Z, Y, X), got {tuple(volume.shape)}")
     code, vol = _device_dtype(torch, volume)
-    return torch, code, (vol if vol.stride(2) == 1 else vol.contiguous())
+    vol, sz, sy = _kernel_view(vol)          # never a zero or overlapping stride (broadcast views are compacted)
+    return torch, code, vol, sz, sy
 
 
 def flat_field_pattern(volume):
     """Per-pixel median over the scan axis, float32 ``(Y, X)`` (``numpy.median`` / ``quantile(0.5)`` semantics)."""
-    torch, code, vol = _prep(volume)
+    torch, code, vol, sz, sy = _prep(volume)
     Z, Y, X = vol.shape
     with torch.cuda.device(vol.device):
         pattern = torch.empty((Y, X), dtype=torch.float32, device=vol.device)
         _cabi.check(_cabi.lib().shrimpy_flatfield_pattern_device(
-            vol.data_ptr(), code, pattern.data_ptr(), Z, Y, X, vol.stride(0), vol.stride(1),
+            vol.data_ptr(), code, pattern.data_ptr(), Z, Y, X, sz, sy,
             torch.cuda.current_stream().cuda_stream))
     return pattern
 
 
 def flat_field_scale(volume):
     """Scale field ``mean(pattern) / pattern`` of a stack, float32 ``(Y, X)``."""
-    torch, _, _ = _prep(volume)
+    torch = _prep(volume)[0]
     pattern = flat_field_pattern(volume)
     with torch.cuda.device(pattern.device):
         scale = torch.empty_like(pattern)
@@ -61,7 +62,7 @@ def flat_field_scale(volume):
 
 def flat_field_BF(volume):
     """Drop-in for ``_LabelfreePreprocessor._flat_field_BF``: corrected float32 volume on the same device."""
-    torch, code, vol = _prep(volume)
+    torch, code, vol, _, _ = _prep(volume)
     vol = vol.contiguous()
     scale = flat_field_scale(vol)
     Z, Y, X = vol.shape
@@ -79,7 +80,7 @@ def deskew_flat_field_zyx(raw_data, ls_angle_deg: float, px_to_scan_ratio: float
     ``scale`` may carry a precomputed scale field (e.g. from a previous timepoint of the same position);
     by default it is computed from ``raw_data`` itself, as the reference does per stack.
     """
-    torch, code, raw = _prep(raw_data)
+    torch, code, raw, raw_sz, raw_sy = _prep(raw_data)
     g = deskew_geometry(tuple(raw.shape), ls_angle_deg, px_to_scan_ratio, keep_overhang, average_n_slices)
     Z, Y, X = g.raw_shape
     if scale is None:
@@ -95,7 +96,7 @@ def deskew_flat_field_zyx(raw_data, ls_angle_deg: float, px_to_scan_ratio: float
             return out
         _cabi.check(_cabi.lib().shrimpy_deskew_flatfield_device(
             raw.data_ptr(), code, scale.data_ptr(), out.data_ptr(), Z, Y, X, g.out_shape[2], g.n_avg,
-            g.m00, g.m02, g.shift, float(cval), raw.stride(0), raw.stride(1),
+            g.m00, g.m02, g.shift, float(cval), raw_sz, raw_sy,
             ctypes.cast(None, ctypes.POINTER(_cabi.Window)), _cabi.KERNELS[kernel],
             torch.cuda.current_stream().cuda_stream))
     return out

@@ -15,10 +15,15 @@ Cutting by bytes rather than by slices is what makes the pieces adjacent: a phys
 multiples of the allocation granularity (2 MiB), and a mantis slice (300 x 2048 uint16 = 1 228 800 B) is not one; the
 slice that straddles a page boundary simply has its head on one GPU and its tail on the next.
 
-Status: the layout arithmetic and the descriptor exchange are covered by CPU tests (``tests/test_paged_stack.py``:
-every byte a rank's columns read is mapped, stitched windows equal the stack, 3-process fd hand-over over unix
-sockets, the whole call sequence against an emulation of the driver's virtual-memory calls).  The driver calls were written after round 1's GPU minutes ran out and have NOT run on a GPU yet:
-``tools/scan_split_bench.py --transport vmm`` is the first thing to run (2 GPUs) before anything relies on it.
+A physical handle can only be mapped WHOLE (``cuMemMap`` wants ``offset == 0``: the first B200 run of this module
+answered ``CUDA_ERROR_NOT_SUPPORTED`` to a partial mapping), so a rank's bytes are not one allocation but a few
+**segments**, cut wherever some rank's window begins or ends: a reader's window is then a union of whole segments, and
+only the segments a neighbour reads are exported.
+
+Covered on CPU (``tests/test_paged_stack.py``): the layout arithmetic (every byte a rank's columns read is mapped,
+windows are tiled by whole segments), stitched windows equal the stack, the 3-process fd hand-over over unix sockets,
+the whole call sequence against an emulation of the driver's virtual-memory calls.  On GPUs:
+``tests/test_paged_stack_gpu.py`` (one device) and ``tools/scan_split_bench.py --transport vmm`` / ``bench.py`` (N > 1).
 """
 
 from __future__ import annotations
@@ -47,7 +52,9 @@ class PagedShard:
     own_bytes: Tuple[int, int]       # bytes of the flattened stack held in this rank's HBM           [lo, hi), page aligned
     window_bytes: Tuple[int, int]    # bytes of the flattened stack visible in this rank's window     [lo, hi), page aligned
     stack_bytes: int                 # Z * frame_bytes: the last page may reach beyond it
-    maps: Tuple[Tuple[int, int, int, int], ...]   # (owner rank, offset in owner's pages, offset in window, size)
+    maps: Tuple[Tuple[int, int, int, int], ...]   # (owner rank, offset in owner's pages, offset in window, size):
+    #                                               each entry is one WHOLE segment of its owner
+    segments: Tuple[Tuple[int, int], ...] = ()    # this rank's bytes as separate physical allocations [lo, hi)
 
     @property
     def remote_bytes(self) -> int:
@@ -70,34 +77,45 @@ def plan_paged_split(g: DeskewGeometry, world_size: int, frame_bytes: int, granu
         edges.append(min(max(s.own_z[0] * frame_bytes // G * G, edges[-1]), total))
     edges.append(total)
     owned = [(edges[i], edges[i + 1]) for i in range(world_size)]
-    shards = []
+    windows = []
     for s in base:
         lo, hi = owned[s.rank]
         if s.need_z[1] > s.need_z[0]:
             need_lo = s.need_z[0] * frame_bytes // G * G
             need_hi = min(-(-s.need_z[1] * frame_bytes // G) * G, total)
-            wlo, whi = (min(lo, need_lo), max(hi, need_hi)) if hi > lo else (need_lo, need_hi)
+            windows.append((min(lo, need_lo), max(hi, need_hi)) if hi > lo else (need_lo, need_hi))
         else:
-            wlo, whi = lo, hi
-        maps = []
-        for r, (a, b) in enumerate(owned):
-            x0, x1 = max(a, wlo), min(b, whi)
-            if x1 > x0:
-                maps.append((r, x0 - a, x0 - wlo, x1 - x0))
-        shards.append(PagedShard(s.rank, s.cols, s.need_z, (lo, hi), (wlo, whi), Z * frame_bytes, tuple(maps)))
+            windows.append((lo, hi))
+    # a handle is mapped whole: cut every rank's bytes wherever any window begins or ends
+    cuts = sorted({v for w in windows for v in w} | set(edges))
+    segments = [tuple((a, b) for a, b in zip(cuts[:-1], cuts[1:]) if lo <= a and b <= hi) for lo, hi in owned]
+    shards = []
+    for s in base:
+        wlo, whi = windows[s.rank]
+        maps = tuple((r, a - owned[r][0], a - wlo, b - a)
+                     for r in range(world_size) for a, b in segments[r] if wlo <= a and b <= whi)
+        shards.append(PagedShard(s.rank, s.cols, s.need_z, owned[s.rank], (wlo, whi), Z * frame_bytes, maps,
+                                 segments[s.rank]))
     return shards
 
 
-def exchange_descriptors(my_fd: int, shards: Sequence[PagedShard], rank: int, group=None) -> Dict[int, int]:
-    """Hand this rank's exported file descriptor to every rank that maps its pages, and collect the descriptors of
-    the ranks whose pages this rank maps (``SCM_RIGHTS`` over unix sockets: a descriptor is only meaningful inside
-    the process that received it this way).  ``my_fd < 0`` means this rank owns no pages.  Returns {owner: fd}."""
+def exchange_descriptors(my_fds: Dict[int, int], shards: Sequence[PagedShard], rank: int,
+                         group=None) -> Dict[Tuple[int, int], int]:
+    """Hand this rank's exported file descriptors (``{offset of the segment in this rank's bytes: fd}``) to every
+    rank that maps one of its segments, and collect the descriptors of the segments this rank maps (``SCM_RIGHTS``
+    over unix sockets: a descriptor is only meaningful inside the process that received it this way).  A client
+    names the segments it wants; the owner answers with exactly those.  Returns ``{(owner, offset): fd}``."""
+    import json
+
     import torch.distributed as dist
 
     token = [uuid.uuid4().hex if rank == 0 else None]
     dist.broadcast_object_list(token, src=0, group=group)
     path = lambda r: f"/tmp/shrimpy_b200_pages_{token[0]}_{r}.sock"     # noqa: E731
-    wanted = [owner for owner, _, _, _ in shards[rank].maps if owner != rank]
+    wanted: Dict[int, List[int]] = {}
+    for owner, h_off, _, _ in shards[rank].maps:
+        if owner != rank:
+            wanted.setdefault(owner, []).append(h_off)
     clients = sum(1 for s in shards if s.rank != rank and any(owner == rank for owner, _, _, _ in s.maps))
     server = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
     server.bind(path(rank))
@@ -109,7 +127,8 @@ def exchange_descriptors(my_fd: int, shards: Sequence[PagedShard], rank: int, gr
             for _ in range(clients):
                 conn, _ = server.accept()
                 with conn:
-                    socket.send_fds(conn, [b"p"], [my_fd])
+                    offsets = json.loads(conn.recv(65536).decode())
+                    socket.send_fds(conn, [b"p"], [my_fds[o] for o in offsets])
         except BaseException as exc:   # surfaced on the caller's thread below
             failure.append(exc)
 
@@ -117,14 +136,16 @@ def exchange_descriptors(my_fd: int, shards: Sequence[PagedShard], rank: int, gr
     try:
         dist.barrier(group=group)              # every listener is bound before anyone connects
         worker.start()
-        got: Dict[int, int] = {}
-        for owner in wanted:
+        got: Dict[Tuple[int, int], int] = {}
+        for owner, offsets in wanted.items():
             with socket.socket(socket.AF_UNIX, socket.SOCK_STREAM) as c:
                 c.connect(path(owner))
-                _, fds, _, _ = socket.recv_fds(c, 16, 1)
-                if len(fds) != 1:
-                    raise RuntimeError(f"rank {owner} sent {len(fds)} descriptors instead of one")
-                got[owner] = fds[0]
+                c.sendall(json.dumps(offsets).encode())
+                _, fds, _, _ = socket.recv_fds(c, 16, len(offsets))
+                if len(fds) != len(offsets):
+                    raise RuntimeError(f"rank {owner} sent {len(fds)} descriptors instead of {len(offsets)}")
+                for o, fd in zip(offsets, fds):
+                    got[(owner, o)] = fd
         worker.join(timeout=120)
         if worker.is_alive() or failure:
             raise RuntimeError(f"descriptor hand-over failed on rank {rank}: {failure or 'peer never connected'}")
@@ -246,8 +267,8 @@ class PagedStack(PagedWindow):
         self.frame_shape, self.dtype, self.device_index = tuple(frame_shape), dtype, int(device_index)
         self.itemsize = torch.empty((), dtype=dtype).element_size()
         self.frame_bytes = self.frame_shape[0] * self.frame_shape[1] * self.itemsize
-        self._handles: Dict[int, object] = {}
-        self._release: List[int] = []          # the handles this object has to release (all but borrowed ones)
+        self._handles: Dict[Tuple[int, int], object] = {}    # (owner, offset of the segment in the owner's bytes)
+        self._release: List[Tuple[int, int]] = []            # the handles this object has to release (not borrowed ones)
         self._local = _local_handles is not None
         self._fds: List[int] = []
         self._va, self._mapped = None, []
@@ -257,28 +278,33 @@ class PagedStack(PagedWindow):
         if (hi - lo) % granularity or (whi - wlo) % granularity:
             raise ValueError("the plan was made for another granularity")
         kind = drv.CUmemAllocationHandleType.CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR
-        my_fd = -1
         try:
-            if self._local:            # every rank's pages were created in this process (``on_one_device``)
+            if self._local:            # every rank's segments were created in this process (``on_one_device``)
                 self._handles = dict(_local_handles)
-                self._release = [rank] if rank in self._handles else []
+                self._release = [k for k in self._handles if k[0] == rank]
             else:
-                if hi > lo:
-                    self._handles[rank] = _ck(drv.cuMemCreate(hi - lo, self.allocation_prop(self.device_index), 0),
-                                              "cuMemCreate")
-                    self._release.append(rank)
-                    my_fd = int(_ck(drv.cuMemExportToShareableHandle(self._handles[rank], kind, 0),
-                                    "cuMemExportToShareableHandle"))
-                    self._fds.append(my_fd)
-                for owner, fd in exchange_descriptors(my_fd, self.shards, rank, group).items():
+                read_by_others = {h_off for s in self.shards if s.rank != rank
+                                  for owner, h_off, _, _ in s.maps if owner == rank}
+                my_fds: Dict[int, int] = {}
+                for a, b in self.shard.segments:
+                    key = (rank, a - lo)
+                    self._handles[key] = _ck(drv.cuMemCreate(b - a, self.allocation_prop(self.device_index), 0),
+                                             "cuMemCreate")
+                    self._release.append(key)
+                    if key[1] in read_by_others:
+                        fd = int(_ck(drv.cuMemExportToShareableHandle(self._handles[key], kind, 0),
+                                     "cuMemExportToShareableHandle"))
+                        my_fds[key[1]] = fd
+                        self._fds.append(fd)
+                for key, fd in exchange_descriptors(my_fds, self.shards, rank, group).items():
                     self._fds.append(fd)
-                    self._handles[owner] = _ck(drv.cuMemImportFromShareableHandle(fd, kind),
-                                               "cuMemImportFromShareableHandle")
-                    self._release.append(owner)
+                    self._handles[key] = _ck(drv.cuMemImportFromShareableHandle(fd, kind),
+                                             "cuMemImportFromShareableHandle")
+                    self._release.append(key)
             if whi > wlo:
                 self._va = int(_ck(drv.cuMemAddressReserve(whi - wlo, granularity, 0, 0), "cuMemAddressReserve"))
-                for owner, h_off, w_off, size in self.shard.maps:
-                    _ck(drv.cuMemMap(self._va + w_off, size, h_off, self._handles[owner], 0), "cuMemMap")
+                for owner, h_off, w_off, size in self.shard.maps:      # every entry is one whole handle: offset 0
+                    _ck(drv.cuMemMap(self._va + w_off, size, 0, self._handles[(owner, h_off)], 0), "cuMemMap")
                     self._mapped.append((self._va + w_off, size))
                 access = drv.CUmemAccessDesc()
                 access.location.type = drv.CUmemLocationType.CU_MEM_LOCATION_TYPE_DEVICE
@@ -321,9 +347,9 @@ class PagedStack(PagedWindow):
         _make_current(device_index)
         handles = {}
         for s in shards:
-            lo, hi = s.own_bytes
-            if hi > lo:
-                handles[s.rank] = _ck(drv.cuMemCreate(hi - lo, cls.allocation_prop(device_index), 0), "cuMemCreate")
+            for a, b in s.segments:
+                handles[(s.rank, a - s.own_bytes[0])] = _ck(
+                    drv.cuMemCreate(b - a, cls.allocation_prop(device_index), 0), "cuMemCreate")
         return [cls(shards, s.rank, frame_shape, dtype, device_index, granularity, _local_handles=handles)
                 for s in shards]
 
@@ -361,8 +387,8 @@ class PagedStack(PagedWindow):
         for ptr, size in self._mapped:
             drv.cuMemUnmap(ptr, size)
         self._mapped = []
-        for owner in self._release:
-            drv.cuMemRelease(self._handles[owner])
+        for key in self._release:
+            drv.cuMemRelease(self._handles[key])
         self._handles, self._release = {}, []
         if self._va is not None:
             wlo, whi = self.shard.window_bytes

@@ -147,18 +147,26 @@ def deskew_plate(src: Sequence[Position], settings, dst: Optional[Sequence[Posit
             return slot
 
         def finish(k: int, slot: int, done):
-            done.synchronize()                      # D2H of this unit landed in h_out[slot]
-            i, t, c = mine[k]
-            result = h_out[slot].numpy()
-            t0 = time.perf_counter()
-            written = dst[i].array.write_stack(t, c, result, pool=io_pool) if dst is not None else 0
-            if on_result is not None:
-                on_result(src[i].name, t, c, result)
-            with lock:
-                stats.disk_write_bytes += written
-                stats.write_seconds += time.perf_counter() - t0
-                stats.per_unit.append((src[i].name, t, c))
-            free[slot].release()
+            try:
+                done.synchronize()                      # D2H of this unit landed in h_out[slot]
+                i, t, c = mine[k]
+                result = h_out[slot].numpy()
+                t0 = time.perf_counter()
+                written = dst[i].array.write_stack(t, c, result, pool=io_pool) if dst is not None else 0
+                if on_result is not None:
+                    on_result(src[i].name, t, c, result)
+                with lock:
+                    stats.disk_write_bytes += written
+                    stats.write_seconds += time.perf_counter() - t0
+                    stats.per_unit.append((src[i].name, t, c))
+            finally:
+                free[slot].release()                    # a failed write must not leave load(k + depth) waiting for ever
+
+        def raise_failed(tails):
+            """Surface a writer's / callback's exception now instead of after (or instead of) the next blocking load."""
+            for f in tails:
+                if f.done() and f.exception() is not None:
+                    raise f.exception()
 
         t_start = time.perf_counter()
         # `pool` runs the per-unit stages (blocked loads never exceed `depth`, so 2*depth+1 workers cannot starve the
@@ -167,6 +175,7 @@ def deskew_plate(src: Sequence[Position], settings, dst: Optional[Sequence[Posit
             loads = {k: pool.submit(load, k) for k in range(min(depth, len(mine)))}
             tails = []
             for k in range(len(mine)):
+                raise_failed(tails)
                 slot = loads.pop(k).result()
                 if k + depth < len(mine):
                     loads[k + depth] = pool.submit(load, k + depth)      # blocks in its thread until the slot frees

@@ -195,6 +195,14 @@ def test_corrupt_frames_fail_with_a_message():
     assert run(bad) == _cabi.EINVAL and b"did not decode" in lib.shrimpy_last_error()
     bad = bytearray(frame); bad[2] = (bad[2] & 0x1F) | (0 << 5)                 # blosclz stream: named, not guessed
     assert run(bad) == _cabi.EINVAL and b"blosclz" in lib.shrimpy_last_error()
+    # header fields are untrusted: sizes near 2^31 must be rejected, not wrapped (int32 arithmetic used to let a
+    # blocksize of INT32_MAX through with a success code)
+    bad = bytearray(frame); bad[8:12] = struct.pack("<i", 2**31 - 1)
+    assert run(bad) == _cabi.EINVAL and b"blocksize" in lib.shrimpy_last_error()
+    bad = bytearray(frame); bad[8:12] = struct.pack("<i", data.nbytes + 2)
+    assert run(bad) == _cabi.EINVAL and b"blocksize" in lib.shrimpy_last_error()
+    bad = bytearray(frame); bad[4:8] = struct.pack("<i", 2**31 - 8); bad[2] |= 0x2   # "stored" frame of ~2 GiB
+    assert run(bad, 2**31 - 8) == _cabi.EINVAL
 
 
 def _acquisition_like(tmp_path, shape, shard, inner, **kw):

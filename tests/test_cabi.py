@@ -1,6 +1,7 @@
 """The C-ABI library loads on a CPU-only box and exports everything include/shrimpy_b200.h declares."""
 
 import ctypes
+import math
 import re
 from pathlib import Path
 
@@ -34,8 +35,11 @@ def test_abi_version_and_no_fallback_message():
 
 
 def test_c_geometry_matches_python():
+    """One code path: Python's geometry IS the C-ABI's trig entry point fed numpy's cos / sin, so they agree with ==;
+    the angle entry point (libm cos / sin) agrees with == whenever libm and numpy return the same two numbers."""
     lib = _cabi.lib()
     rng = np.random.default_rng(1)
+    libm_differs = 0
     for _ in range(300):
         Z, Y, X = (int(v) for v in rng.integers(1, 900, 3))
         th, r = round(float(rng.uniform(1, 45)), 2), round(float(rng.uniform(0.2, 1.2)), 3)
@@ -43,12 +47,25 @@ def test_c_geometry_matches_python():
         shape = (ctypes.c_int64 * 3)()
         vox = (ctypes.c_double * 3)()
         row = (ctypes.c_double * 3)()
-        assert lib.shrimpy_deskew_geometry(Z, Y, X, th, r, keep, n, 0.116, shape, vox, row) == 0
+        theta = th * np.pi / 180
+        ct, st = float(np.cos(theta)), float(np.sin(theta))
+        assert lib.shrimpy_deskew_geometry_trig(Z, Y, X, ct, st, r, keep, n, 0.116, shape, vox, row) == 0
         g = sb.deskew_geometry((Z, Y, X), th, r, bool(keep), n, 0.116)
         assert tuple(shape) == g.out_shape
-        assert row[1] == g.m02 and row[2] == g.shift
-        assert row[0] == pytest.approx(g.m00, rel=1e-15)     # libm cos vs numpy cos: <= 1 ulp
-        assert tuple(vox) == pytest.approx(g.voxel_size, rel=1e-15)
+        assert (row[0], row[1], row[2]) == (g.m00, g.m02, g.shift)
+        assert tuple(vox) == g.voxel_size
+        # the same numbers as the upstream numpy expressions, bit for bit
+        assert g.m00 == -r * np.cos(theta) and g.voxel_size[0] == n * np.sin(theta) * 0.116
+        assert g.shift == (0 if keep else int(np.floor(Y * np.cos(theta) * r)))
+        assert g.out_shape[2] == max(0, int(np.ceil(Z / r + Y * np.cos(theta)) if keep else np.ceil(Z / r - Y * np.cos(theta))))
+        assert lib.shrimpy_deskew_geometry(Z, Y, X, th, r, keep, n, 0.116, shape, vox, row) == 0
+        if math.cos(theta) == ct and math.sin(theta) == st:
+            assert tuple(shape) == g.out_shape and (row[0], row[1], row[2]) == (g.m00, g.m02, g.shift)
+            assert tuple(vox) == g.voxel_size
+        else:
+            libm_differs += 1
+            assert row[0] == pytest.approx(g.m00, rel=2e-16) and tuple(vox) == pytest.approx(g.voxel_size, rel=2e-16)
+    assert libm_differs <= 300    # informational: how often libm and numpy disagree in the last bit on this machine
 
 
 def test_argument_errors_surface_without_a_gpu():

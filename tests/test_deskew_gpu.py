@@ -273,9 +273,6 @@ def test_padded_row_output_is_the_same_volume(torch, sb, n, keep, kernel):
         sb.deskew_zyx(raw, 30.0, 0.39, keep, n, out=out, value_range=torch.empty(2, device="cuda"))
 
 
-@pytest.mark.skipif(not __import__("os").environ.get("SHRIMPY_TEST_UNMEASURED"),
-                    reason="kernel='tma_aligned' was written after round 1's GPU minutes ran out: first run "
-                           "tools/probe/aligned_rows_probe.py on a B200, then drop this gate")
 @pytest.mark.parametrize("shape,r,keep,n", [((90, 13, 128), 0.39, False, 1), ((120, 31, 200), 0.39, True, 3),
                                             ((120, 31, 200), 0.651, False, 4), ((300, 40, 264), 1.3, True, 1)])
 def test_whole_sector_spans_variant_is_the_same_volume(torch, sb, shape, r, keep, n):
@@ -288,3 +285,85 @@ def test_whole_sector_spans_variant_is_the_same_volume(torch, sb, shape, r, keep
     assert torch.equal(got, want)
     with pytest.raises(Exception):
         sb.deskew_zyx(raw, 30.0, r, keep, n, kernel="tma_aligned", value_range=torch.empty(2, device="cuda"))
+
+
+def test_broadcast_and_odd_stride_views_are_compacted_not_misread(torch, sb, oracle):
+    """A broadcast stack (stride 0 along z) used to reach the C-ABI as "stride 0 = contiguous default" and read
+    Z*Y*X elements from a Y*X allocation; every view now deskews to the same volume as its compact copy."""
+    plane = torch.from_numpy(synthetic_stack((1, 12, 64), seed=40)[0]).cuda()
+    view = plane[None].expand(50, 12, 64)
+    assert view.stride(0) == 0
+    want = sb.deskew_zyx(view.contiguous(), 30.0, 0.39, True, 2)
+    assert torch.equal(sb.deskew_zyx(view, 30.0, 0.39, True, 2), want)
+    raw = torch.from_numpy(synthetic_stack((40, 12, 64), seed=41)).cuda()
+    for v in (raw.permute(0, 2, 1).contiguous().permute(0, 2, 1),      # x not the fastest axis
+              raw.flip(0),                                             # negative-stride-like copy (torch makes it dense)
+              raw[::2],                                                # every other slice: stride_z = 2*Y*X, no copy
+              raw[:, ::3]):                                            # every third row:   stride_y = 3*X, no copy
+        assert torch.equal(sb.deskew_zyx(v, 30.0, 0.39, False, 1), sb.deskew_zyx(v.contiguous(), 30.0, 0.39, False, 1))
+    from shrimpy_b200 import flatfield
+    assert torch.equal(flatfield.flat_field_pattern(view), plane.to(torch.float32))
+    with pytest.raises(ValueError):
+        sb.deskew_window(raw, sb.deskew_geometry((40, 12, 64), 30.0, 0.39, True, 1), p_begin=0, p_count=12, c_begin=0,
+                         c_count=32, y_origin=0, z_origin=0, out=torch.empty((12, 32, 64), device="cuda").transpose(1, 2))
+
+
+def test_cval_none_on_an_x_chunk_view_pads_with_the_chunk_minimum(torch, sb, oracle):
+    """``cval=None`` pads with min(raw) of the VIEW (what deskew_data's ``raw.min()`` sees), not of the 128
+    consecutive-in-memory columns the un-compacted reduction used to walk."""
+    raw = synthetic_stack((48, 9, 256), seed=42)
+    raw[:, :, :64] = 5                     # a smaller value outside the chunk
+    chunk = torch.from_numpy(raw).cuda()[:, :, 128:256]
+    assert not chunk.is_contiguous()
+    got = sb.deskew_zyx(chunk, 30.0, 0.39, True, 1, cval=None).cpu().numpy()
+    want = oracle[0].deskew_data(raw[:, :, 128:256], 30.0, 0.39, True, 1, cval=None)
+    assert float(got.min()) == float(raw[:, :, 128:256].min()) != 5.0
+    assert np.array_equal(got == got.min(), want == want.min())
+    assert_close_range(got, want, TIGHT_TOL, "cval=None on a view")
+    assert np.array_equal(got, sb.deskew_data(raw[:, :, 128:256], 30.0, 0.39, True, 1, cval=None))
+
+
+def test_pageable_and_pinned_callers_get_the_same_bytes(torch, sb):
+    """numpy in / numpy out as scripts/measure_psf.py:239-246 calls it: an ordinary (pageable) array goes through the
+    pipeline's own page-locked staging rings, a pinned one is copied directly; same result, and the staging really ran."""
+    from shrimpy_b200 import _cabi
+    from shrimpy_b200.deskew import _pipeline_for
+    import ctypes
+
+    raw = synthetic_stack((300, 60, 512), seed=43)
+    pinned_in = torch.from_numpy(raw).pin_memory()
+    g = sb.deskew_geometry(raw.shape, 30.0, 0.39, False, 3)
+    pinned_out = torch.empty(g.out_shape, dtype=torch.float32).pin_memory()
+    a = sb.deskew_data(pinned_in.numpy(), 30.0, 0.39, False, 3, out=pinned_out.numpy())
+    pipe = _pipeline_for(torch.cuda.current_device())
+    si, so = ctypes.c_int64(), ctypes.c_int64()
+
+    def staged():
+        _cabi.check(_cabi.lib().shrimpy_pipeline_staged_bytes(pipe._handle, ctypes.byref(si), ctypes.byref(so)))
+        return si.value, so.value
+
+    assert staged() == (0, 0)
+    b = sb.deskew_data(raw, 30.0, 0.39, False, 3, out=np.empty(g.out_shape, np.float32))
+    assert staged() == (raw.nbytes, b.nbytes)
+    c = sb.deskew_data(raw, 30.0, 0.39, False, 3)                  # default result: torch's pinned cache
+    assert staged() == (raw.nbytes, 0)
+    dev = sb.deskew_zyx(torch.from_numpy(raw).cuda(), 30.0, 0.39, False, 3).cpu().numpy()
+    assert np.array_equal(a, dev) and np.array_equal(b, dev) and np.array_equal(c, dev)
+
+
+def test_two_threads_calling_deskew_data_on_one_gpu(torch, sb):
+    """An IO pool over positions: each thread gets its own pipeline (slots, streams, events), and one pipeline that IS
+    shared is serialised inside the C-ABI -- either way every call returns its own volume."""
+    from concurrent.futures import ThreadPoolExecutor
+    from shrimpy_b200.deskew import HostPipeline
+
+    stacks = [synthetic_stack((200, 30, 256), seed=50 + i) for i in range(4)]
+    want = [sb.deskew_zyx(torch.from_numpy(s).cuda(), 30.0, 0.39, False, 3).cpu().numpy() for s in stacks]
+    with ThreadPoolExecutor(4) as pool:
+        for _ in range(3):
+            got = list(pool.map(lambda s: sb.deskew_data(s, 30.0, 0.39, False, 3), stacks))
+            assert all(np.array_equal(g, w) for g, w in zip(got, want))
+    g = sb.deskew_geometry(stacks[0].shape, 30.0, 0.39, False, 3)
+    with HostPipeline(torch.cuda.current_device()) as shared, ThreadPoolExecutor(4) as pool:
+        got = list(pool.map(lambda s: shared.deskew(s, g, 0.0), stacks * 2))
+    assert all(np.array_equal(g_, w) for g_, w in zip(got, want * 2))

@@ -44,6 +44,11 @@ def test_plan_partitions_the_stack_into_pages_and_maps_every_needed_byte(world, 
             assert lo + h_off == wlo + w_off and lo + h_off + size <= hi
             at += size
         assert at == whi - wlo
+        # a handle is only ever mapped whole: every map is exactly one segment of its owner
+        for owner, h_off, _, size in s.maps:
+            lo = shards[owner].own_bytes[0]
+            assert (lo + h_off, lo + h_off + size) in shards[owner].segments
+        assert sum(b - a for a, b in s.segments) == s.own_bytes[1] - s.own_bytes[0]
         if world > 1:
             # the halo: about r*cos(theta)*(Y-1)+1 slices below, two above, rounded out to pages
             assert s.remote_bytes <= (int(0.39 * np.cos(np.pi / 6) * 299) + 5) * F + 3 * granularity
@@ -119,16 +124,20 @@ def _fd_worker(rank, world, port, outdir):
     try:
         g = sb.deskew_geometry((4000, 30, 64), 30.0, 0.39, True, 1)
         shards = ps.plan_paged_split(g, world, 30 * 64 * 2, 64 << 10)
-        fd = os.memfd_create(f"pages{rank}")            # stands for the exported CUDA allocation handle
-        os.write(fd, f"pages of rank {rank}".encode())
-        got = ps.exchange_descriptors(fd, shards, rank)
-        assert sorted(got) == sorted(owner for owner, _, _, _ in shards[rank].maps if owner != rank)
-        for owner, peer_fd in got.items():
-            assert os.pread(peer_fd, 64, 0) == f"pages of rank {owner}".encode()
+        lo = shards[rank].own_bytes[0]
+        mine = {}
+        for a, b in shards[rank].segments:              # memfds stand for the exported CUDA allocation handles
+            mine[a - lo] = os.memfd_create(f"pages{rank}_{a - lo}")
+            os.write(mine[a - lo], f"segment {a - lo} of rank {rank}".encode())
+        got = ps.exchange_descriptors(mine, shards, rank)
+        assert sorted(got) == sorted((owner, off) for owner, off, _, _ in shards[rank].maps if owner != rank)
+        for (owner, off), peer_fd in got.items():
+            assert os.pread(peer_fd, 64, 0) == f"segment {off} of rank {owner}".encode()
             os.close(peer_fd)
-        os.close(fd)
+        for fd in mine.values():
+            os.close(fd)
         with open(os.path.join(outdir, f"ok{rank}"), "w") as f:
-            f.write(str(len(got)))
+            f.write(str(len({owner for owner, _ in got})))
     finally:
         dist.destroy_process_group()
 
@@ -164,6 +173,7 @@ class EmulatedDriver:
 
         self._real = driver
         self.storage, self.mappings, self.reserved, self.access, self.released = {}, [], {}, [], []
+        self._arena, self._arena_used, self._arena_at = np.zeros(64 << 20, dtype=np.uint8), 0, {}
         self._next_handle, self._next_va = 1, 0x7F0000000000
 
     def __getattr__(self, name):
@@ -177,7 +187,12 @@ class EmulatedDriver:
         assert size > 0 and size % 4096 == 0 and flags == 0
         assert prop.location.type == self._real.CUmemLocationType.CU_MEM_LOCATION_TYPE_DEVICE
         handle, self._next_handle = self._next_handle, self._next_handle + 1
-        self.storage[handle] = np.zeros(size, dtype=np.uint8)
+        # handles created one after the other are neighbours in one arena, so that a run of a rank's segments
+        # mapped side by side can be handed out as ONE writable host view (what `own` is on the device)
+        self.storage[handle] = self._arena[self._arena_used:self._arena_used + size]
+        self._arena_at[handle] = self._arena_used
+        self._arena_used += size
+        assert self._arena_used <= self._arena.size
         return (self._real.CUresult.CUDA_SUCCESS, handle)
 
     def cuMemAddressReserve(self, size, alignment, addr, flags):
@@ -188,7 +203,7 @@ class EmulatedDriver:
     def cuMemMap(self, ptr, size, offset, handle, flags):
         base = max(v for v in self.reserved if v <= ptr)
         assert ptr + size <= base + self.reserved[base], "mapping outside the reserved range"
-        assert offset % 4096 == 0 and size % 4096 == 0 and offset + size <= self.storage[handle].size
+        assert offset == 0 and size == self.storage[handle].size, "the driver maps whole handles only (offset 0)"
         assert all(ptr + size <= p or p + n <= ptr for p, n, _, _ in self.mappings), "address mapped twice"
         self.mappings.append((ptr, size, handle, offset))
         return (self._real.CUresult.CUDA_SUCCESS,)
@@ -212,10 +227,15 @@ class EmulatedDriver:
 
     # what the hardware does with the mappings
     def view(self, ptr, nbytes):
-        for p, n, handle, offset in self.mappings:
-            if p <= ptr and ptr + nbytes <= p + n:
-                return self.storage[handle][offset + ptr - p:offset + ptr - p + nbytes]
-        raise AssertionError("range is not inside one mapping")
+        at, start = ptr, None
+        while at < ptr + nbytes:
+            p, n, handle, offset = next(m for m in self.mappings if m[0] <= at < m[0] + m[1])
+            here = self._arena_at[handle] + offset + at - p
+            if start is None:
+                start = here
+            assert here == start + (at - ptr), "the mapped handles are not neighbours in the arena"
+            at = p + n
+        return self._arena[start:start + nbytes]
 
     def read(self, ptr, nbytes):
         out = np.empty(nbytes, dtype=np.uint8)

@@ -1,17 +1,11 @@
 """Byte-paged scan split on ONE GPU: every rank's pages in one process, windows stitched with cuMemMap, the window
-kernel reading through a stitched range.  Gated: ``paged_stack.py`` was written after round 1's GPU minutes ran out;
-run ``SHRIMPY_TEST_UNMEASURED=1 python -m pytest tests/test_paged_stack_gpu.py`` on a B200 first, then drop the gate."""
+kernel reading through a stitched range (the driver maps whole handles only, hence the segments of the plan)."""
 
-import os
-
-import numpy as np
 import pytest
 
 from helpers import synthetic_stack
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(not os.environ.get("SHRIMPY_TEST_UNMEASURED"),
-                                 reason="not yet run on a GPU (see the module docstring)")]
+pytestmark = [pytest.mark.gpu]
 
 
 @pytest.mark.parametrize("world,keep,n", [(1, True, 1), (3, True, 1), (4, False, 3)])
