@@ -11,9 +11,15 @@ ours       ``value``  device-resident: inputs already in HBM, K steps timed with
                       launching stream; one deskew_tma_kernel launch per channel.
            ``e2e``    the same metric through the public numpy API (``shrimpy_b200.deskew_data``:
                       pinned host stack in, pinned host result out, H2D and D2H inside the timed
-                      region).
-           ``roofline``      algorithmic bytes / measured launch time vs MEASURED_PEAKS.json
-           ``cpu_baseline``  the scipy reference form on the box's host cores, bounded sample
+                      region), with the copy-only ``floor`` of the box at this many ranks beside it and
+                      the ``pageable`` / ``online`` forms a reference caller gets.
+           ``roofline``      algorithmic bytes / measured launch time vs MEASURED_PEAKS.json, burst (the K
+                             steps) and ``sustained`` (>= 1000 launches), also on the bytes that must move
+           ``scan_split``    BASELINE.json configs[4]: one oversized volume split along the scan axis over
+                             the N ranks, halo over NVLink, bit-equal to the single-GPU window
+           ``plate``         BASELINE.json configs[3]: 96 x 10 stacks streamed from an OME-Zarr store in RAM
+           ``affine_registration`` (N=1)  BASELINE.json configs[2]
+           ``cpu_baseline``  (N=1)  the scipy reference form on the box's host cores, bounded sample
 reference  the reference's own CPU form (scipy.ndimage.affine_transform + edge-padded mean, X-chunked
            over all host cores like scripts/measure_psf.py:218-249), same metric and config.
 
@@ -185,11 +191,27 @@ def run_reference(args):
 # --------------------------------------------------------------------------------------------------
 # our arm
 # --------------------------------------------------------------------------------------------------
+def needed_input_voxels(g):
+    """Raw voxels the deskew actually addresses: for every tilt row the scan slices between the taps of its first
+    and last inside output column (with keep_overhang=False the head and tail of every row's scan range are never
+    read -- 16 % of the mantis stack)."""
+    Z, Y, X = g.raw_shape
+    Xp = g.out_shape[2]
+    o0 = np.arange(Y, dtype=np.float64)
+    base = g.shift + o0 * g.m00
+    first, last = base + 0.0 * g.m02, base + (Xp - 1) * g.m02
+    live = (last >= 0) & (first <= Z - 1)
+    lo = np.floor(np.clip(first, 0, Z - 1))
+    hi = np.minimum(np.floor(np.clip(last, 0, Z - 1)) + 1, Z - 1)
+    return int(np.sum((hi - lo + 1)[live])) * X
+
+
 def run_ours(args):
     import torch
 
     import shrimpy_b200 as sb
     from shrimpy_b200 import _cabi
+    from tools import bench_blocks
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -208,15 +230,23 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     if args.gpus != world and rank == 0:
         print(f"[bench] --gpus {args.gpus} but WORLD_SIZE={world}; using {world}", file=sys.stderr)
+    blocks = set(args.blocks.split(","))
 
     def barrier():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def max_over_ranks(v):
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     g = sb.deskew_geometry(RAW_SHAPE, ANGLE, RATIO, KEEP, NAVG)
     vox_in, vox_out = g.algorithmic_bytes
     alg_bytes = vox_in * 2 + vox_out * 4
+    needed_bytes = needed_input_voxels(g) * 2 + vox_out * 4
 
     # ---- synthetic inputs resident in HBM (seeded per rank and channel) ----------------------------
     gen = torch.Generator(device="cuda").manual_seed(1 + rank)
@@ -228,56 +258,28 @@ def run_ours(args):
         for c in range(CHANNELS):
             sb.deskew_zyx(raws[c], ANGLE, RATIO, KEEP, NAVG, out=outs[c])
 
+    def timed_steps(n):
+        barrier()
+        start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with ClockSampler(local) as clocks:
+            start.record()
+            for _ in range(n):
+                step()
+            stop.record()
+            barrier()
+        return max_over_ranks(start.elapsed_time(stop)), clocks.summary()
+
     for _ in range(max(args.warmup, 3)):
         step()
-    barrier()
-    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches0 = _cabi.launch_count()
-    with ClockSampler(local) as clocks:
-        start.record()
-        for _ in range(args.steps):
-            step()
-        stop.record()
-        barrier()
+    ms_total, clocks = timed_steps(args.steps)
     launches = _cabi.launch_count() - launches0
-    ms_total = torch.tensor([start.elapsed_time(stop)], dtype=torch.float64, device="cuda")
-    if dist is not None:
-        dist.all_reduce(ms_total, op=dist.ReduceOp.MAX)
-    ms_total = float(ms_total.item())
     value = world * CHANNELS * vox_out * args.steps / (ms_total * 1e-3) / 1e9
     kernel_ms = ms_total / (args.steps * CHANNELS)      # the region holds only these launches, back to back
-
-    # ---- end to end through the public numpy API, pinned host buffers ------------------------------
-    e2e_steps = max(1, min(args.steps, 8))
-    h_raw = [torch.empty(RAW_SHAPE, dtype=torch.uint16).pin_memory() for _ in range(CHANNELS)]
-    h_out = [torch.empty(g.out_shape, dtype=torch.float32).pin_memory() for _ in range(CHANNELS)]
-    for c in range(CHANNELS):
-        h_raw[c].copy_(raws[c])
-    np_raw = [t.numpy() for t in h_raw]
-    np_out = [t.numpy() for t in h_out]
-
-    def e2e_step():
-        for c in range(CHANNELS):
-            sb.deskew_data(np_raw[c], ANGLE, RATIO, KEEP, NAVG, device=f"cuda:{local}", out=np_out[c])
-
-    e2e_step()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        e2e_step()          # synchronous: returns when the host result is complete
-    barrier()
-    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
-    if dist is not None:
-        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-    e2e_s = float(e2e_s.item())
-    e2e_value = world * CHANNELS * vox_out * e2e_steps / e2e_s / 1e9
-    e2e_ok = bool(torch.equal(h_out[0], outs[0].cpu()))
-
-    if dist is not None:
-        dist.barrier()
-        dist.destroy_process_group()
-    if rank != 0:
-        return 0
+    # the same launch sustained: >= 1000 launches back to back (the board reaches its power cap after ~0.1 s)
+    sus_steps = max(500, args.steps)
+    sus_ms, sus_clocks = timed_steps(sus_steps)
+    sus_kernel_ms = sus_ms / (sus_steps * CHANNELS)
 
     peak, peak_src = measured_peak()
     achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
@@ -295,71 +297,58 @@ def run_ours(args):
         "roofline": {
             "bound": "hbm", "kernel": "deskew_tma_kernel<uint16,3>", "achieved": achieved, "peak": peak, "unit": "GB/s",
             "frac": achieved / peak, "peak_source": peak_src, "traffic": ncu_traffic(),
+            "traffic_source": "static: dram__bytes_read.sum + dram__bytes_write.sum of one launch in the committed ncu "
+                              "--set full capture (profiles/roofline_traffic.json), not measured in this run",
             "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": kernel_ms,
-        },
-        "e2e": {
-            "value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": CHANNELS * vox_in * 2,
-            "d2h_bytes_per_step": CHANNELS * vox_out * 4, "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps,
-            "api": "shrimpy_b200.deskew_data(numpy pinned) -> shrimpy_deskew_host (H2D | kernel | D2H on 3 streams)",
-            "matches_device_path": e2e_ok, "numa_bound": numa_bound,
+            "needed_bytes_per_launch": needed_bytes,
+            "frac_needed_bytes": needed_bytes / (kernel_ms * 1e-3) / 1e9 / peak,
+            "needed_bytes_note": "input voxels the kernel addresses (keep_overhang=False never reads the head and tail of "
+                                 "a tilt row's scan range) x 2 + output voxels x 4",
+            "sustained": {"launches": sus_steps * CHANNELS, "launch_ms": sus_kernel_ms,
+                          "achieved": alg_bytes / (sus_kernel_ms * 1e-3) / 1e9,
+                          "frac": alg_bytes / (sus_kernel_ms * 1e-3) / 1e9 / peak,
+                          "frac_needed_bytes": needed_bytes / (sus_kernel_ms * 1e-3) / 1e9 / peak, "clocks": sus_clocks},
         },
         "gpu_launches": int(launches),
-        "clocks": clocks.summary(),
+        "clocks": clocks,
     }
-    if world == 1:
-        del raws, outs, h_raw, h_out
+
+    # ---- end to end through the public numpy API ---------------------------------------------------
+    if "e2e" in blocks:
+        step()
+        torch.cuda.synchronize()
+        line["e2e"] = bench_blocks.e2e_block(dist, rank, world, local, raws, outs, (ANGLE, RATIO, KEEP, NAVG),
+                                             max(2, min(args.steps, 8)), numa_bound)
+    del raws, outs
+    torch.cuda.empty_cache()
+
+    # ---- the two multi-GPU rows of BASELINE.json that are not independent replicas ------------------
+    if "scan" in blocks:
+        try:
+            line["scan_split"] = bench_blocks.scan_split_block(dist, rank, world, local, peak,
+                                                               transports=tuple(args.scan_transports.split(",")))
+        except Exception as exc:      # noqa: BLE001
+            line["scan_split"] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
         torch.cuda.empty_cache()
-        line["affine_registration"] = affine_block(peak)
-    if world == 1 and not args.no_cpu_baseline:
+    if "plate" in blocks:
+        try:
+            line["plate"] = bench_blocks.plate_block(dist, rank, world, local, positions=args.plate_positions,
+                                                     timepoints=args.plate_timepoints)
+        except Exception as exc:      # noqa: BLE001
+            line["plate"] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+        torch.cuda.empty_cache()
+
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank != 0:
+        return 0
+    if world == 1 and "affine" in blocks:
+        line["affine_registration"] = bench_blocks.affine_block(peak)
+    if world == 1 and "cpu" in blocks and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline_block()
     print(json.dumps(line), flush=True)
     return 0
-
-
-def affine_block(peak):
-    """BASELINE.json configs[2] beside the headline: float32 (107, 2048, 2048) resampled with a 4x4 matrix, device
-    resident, CUDA events, median of 8 launches after 3 warm-ups (inputs + outputs of 2.8-3.6 GB exceed the L2)."""
-    import torch
-
-    from shrimpy_b200 import register
-
-    shape = (107, 2048, 2048)
-    vol = torch.randn(shape, device="cuda")
-    a, b, c = np.deg2rad([2.0, 1.0, 3.0])
-    Rz = np.array([[1, 0, 0], [0, np.cos(a), -np.sin(a)], [0, np.sin(a), np.cos(a)]])
-    Ry = np.array([[np.cos(b), 0, np.sin(b)], [0, 1, 0], [-np.sin(b), 0, np.cos(b)]])
-    Rx = np.array([[np.cos(c), -np.sin(c), 0], [np.sin(c), np.cos(c), 0], [0, 0, 1]])
-    Mg = np.eye(4)
-    Mg[:3, :3] = Rz @ Ry @ Rx @ np.diag([1.03, 0.97, 1.1])
-    Mg[:3, 3] = [0.4, -1.2, 2.3]
-    M90 = np.array([[1.0, 0, 0, 3.5], [0, 0, -1.288, 2040.0], [0, 1.288, 0, -20.0], [0, 0, 0, 1]])
-    M90t = M90.copy()
-    M90t[0, 1:3] = [0.02, -0.015]
-    M90t[1, 0], M90t[2, 0] = 0.03, -0.02
-    cases = (("in_plane_identity_like", np.eye(4), shape, "affine_stream_kernel"),
-             ("in_plane_rot90_x1.288_onto_deskewed_grid", M90, (100, 2048, 1279), "affine_stream_kernel (lanes along o1)"),
-             ("general_rot_2_1_3_deg_aniso_scale", Mg, shape, "affine_tilt_kernel"),
-             ("rot90_x1.288_with_tilt_onto_deskewed_grid", M90t, (100, 2048, 1279), "affine_tilt_kernel (lanes along o1)"))
-    res = {}
-    for name, M, oshape, kern in cases:
-        out = torch.empty(oshape, device="cuda")
-        for _ in range(3):
-            register.affine_transform_zyx(vol, M, oshape, out=out)
-        torch.cuda.synchronize()
-        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(8)]
-        for e0, e1 in ev:
-            e0.record()
-            register.affine_transform_zyx(vol, M, oshape, out=out)
-            e1.record()
-        torch.cuda.synchronize()
-        ms = float(np.median([e0.elapsed_time(e1) for e0, e1 in ev]))
-        nbytes = (vol.numel() + out.numel()) * 4
-        res[name] = {"kernel": kern, "out_shape": list(oshape), "ms": ms, "gvoxel_out_per_s": out.numel() / ms / 1e6,
-                     "algorithmic_gbs": nbytes / ms / 1e6, "frac_of_hbm_peak": nbytes / ms / 1e6 / peak,
-                     "inside_fraction": float((out != 0).float().mean())}
-        del out
-    return {"workload": "affine registration resample of a float32 label-free volume (107,2048,2048) with a 4x4 matrix "
-                        "(BASELINE.json configs[2]); algorithmic bytes = (input + output voxels) x 4", "cases": res}
 
 
 def main():
@@ -369,6 +358,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the bounded scipy sample (dev runs)")
+    ap.add_argument("--blocks", default="e2e,scan,plate,affine,cpu",
+                    help="which blocks to run beside the headline (dev runs): e2e,scan,plate,affine,cpu")
+    ap.add_argument("--scan-transports", default="peer,nccl,vmm")
+    ap.add_argument("--plate-positions", type=int, default=96)
+    ap.add_argument("--plate-timepoints", type=int, default=10)
     args = ap.parse_args()
     if args.steps < 1:
         raise SystemExit("--steps must be >= 1")
