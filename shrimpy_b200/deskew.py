@@ -20,7 +20,9 @@ from __future__ import annotations
 
 import ctypes
 import math
+import os
 import threading
+import weakref
 from dataclasses import dataclass
 from typing import Optional, Sequence, Tuple, Union
 
@@ -416,16 +418,44 @@ def deskew_data(raw_data: np.ndarray, ls_angle_deg: float, px_to_scan_ratio: flo
     return _pipeline_for(dev.index).deskew(raw, g, fill, out)
 
 
+_pinned_lock = threading.Lock()
+_pinned_live = 0        # bytes of page-locked results currently held by callers
+
+
+def _pinned_budget() -> int:
+    return int(os.environ.get("SHRIMPY_PINNED_RESULT_BYTES", 4 << 30))
+
+
+def _pinned_release(nbytes: int) -> None:
+    global _pinned_live
+    with _pinned_lock:
+        _pinned_live -= nbytes
+
+
 def _empty_pinned_result(torch, shape) -> np.ndarray:
     """Result array of a numpy-in/numpy-out call, taken from torch's caching pinned-host allocator.
 
-    The device-to-host copy is the stage that bounds the host path and it only runs
-    asynchronously, at the full PCIe rate, into page-locked memory; a pageable ``np.empty`` would make every slab's copy
-    a staged, blocking one.  The array is an ordinary float32 ndarray whose base keeps the block alive; when the caller
-    drops it the block returns to torch's cache, so a loop over chunks or positions pins memory once.  Falls back to
-    pageable memory when the host refuses to lock that much.
+    The device-to-host copy is the stage that bounds the host path and it runs at the full PCIe
+    rate straight into page-locked memory (B200: 32 ms per mantis channel against 48 ms through the pipeline's staging
+    ring into a pageable array).  The array is an ordinary float32 ndarray whose base keeps the block alive; when the
+    caller drops it the block returns to torch's cache, so a loop over chunks or positions that consumes each result
+    pins memory once.  Page-locking NEW memory is slow (hundreds of ms per GB), so a caller that keeps every result
+    (``scripts/measure_psf.py:239-249`` collects the chunks in a list) must not pin without bound: at most
+    ``SHRIMPY_PINNED_RESULT_BYTES`` (default 4 GiB) of results are page-locked at a time, the rest are ordinary arrays
+    filled through the staging ring.  Falls back to pageable memory when the host refuses to lock that much.
     """
-    try:
-        return torch.empty(tuple(shape), dtype=torch.float32, pin_memory=True).numpy()
-    except RuntimeError:
+    global _pinned_live
+    nbytes = 4 * int(np.prod(shape))
+    with _pinned_lock:
+        take = _pinned_live + nbytes <= _pinned_budget()
+        if take:
+            _pinned_live += nbytes
+    if not take:
         return np.empty(shape, dtype=np.float32)
+    try:
+        block = torch.empty(tuple(shape), dtype=torch.float32, pin_memory=True)
+    except RuntimeError:
+        _pinned_release(nbytes)
+        return np.empty(shape, dtype=np.float32)
+    weakref.finalize(block, _pinned_release, nbytes)
+    return block.numpy()

@@ -429,7 +429,7 @@ class ZarrArray:
         Z, zc = self.shape[2], self.chunks[2]
         return [((t, c, k, 0, 0), slice(k * zc, min((k + 1) * zc, Z))) for k in range(-(-Z // zc))]
 
-    def read_stack_into(self, t: int, c: int, out: np.ndarray, pool=None, piece_bytes: int = 32 << 20) -> int:
+    def read_stack_into(self, t: int, c: int, out: np.ndarray, pool=None, piece_bytes: int = 8 << 20) -> int:
         """Read the ``(Z, Y, X)`` stack of ``(t, c)`` into ``out``; z-chunks land in place. Returns disk bytes.
 
         With ``pool`` (a ``ThreadPoolExecutor``) the work is cut into independent pieces -- byte ranges of
