@@ -4,7 +4,7 @@ alone and both at once, all ranks at the same time, no kernel.  Run alone or und
     python tools/pcie_probe.py
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 tools/pcie_probe.py
 
-Buffers have the sizes of one mantis FOV channel pair (1.47 GB up, 2.10 GB down per repetition).  ``--numa 0`` skips
+Buffers have the sizes of one mantis FOV channel pair (1.47 GB up, 2.10 GB down per repetition).  ``--bind 0`` skips
 the CPU-affinity binding of ``hostmem.bind_to_gpu`` so that its effect can be seen; ``--stagger-ms`` starts rank r that
 many milliseconds x r late.  The same measurement is the ``e2e.floor`` block of every ``bench.py`` line.
 """
@@ -20,14 +20,14 @@ sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 import torch
 
 ap = argparse.ArgumentParser()
-ap.add_argument("--numa", type=int, default=1)
+ap.add_argument("--bind", type=int, default=1)
 ap.add_argument("--reps", type=int, default=6)
 ap.add_argument("--stagger-ms", type=float, default=0.0)
 args = ap.parse_args()
 world, rank, local = (int(os.environ.get(k, d)) for k, d in (("WORLD_SIZE", "1"), ("RANK", "0"), ("LOCAL_RANK", "0")))
 torch.cuda.set_device(local)
 bound = False
-if args.numa and world > 1:
+if args.bind and world > 1:
     from shrimpy_b200.hostmem import bind_to_gpu
 
     bound = bind_to_gpu(local)
