@@ -518,6 +518,237 @@ __global__ void __launch_bounds__(kTmaThreads, 4)
     }
 }
 
+// ---- staged variant: whole-sector, 16-byte vector stores into rows of ANY pitch ---------------------------------------
+//
+// The kernel above stores straight from registers: a warp's 32 lanes write 32 consecutive floats of one output row.
+// When a row is not a whole number of 32-byte sectors long (Xp = 1279, 1799, 10517: every mantis geometry), every row
+// starts at another offset inside a sector, each of those 128-byte warp stores straddles sector boundaries, and the
+// write-dominated deskews lose a quarter of their bandwidth to partial-sector writes (measured: the same launch into
+// rows padded to whole sectors runs 0.83 -> 0.64 ms; overlapping the tiles so that tile edges fall on sector
+// boundaries -- ALIGNED above -- recovers only 6 % of it, because the seven warp boundaries inside a tile stay ragged).
+//
+// Here a chunk's results (EPC output rows x 256 columns) go through shared memory and leave as 16-byte stores that
+// start on 32-byte boundaries of global memory, whatever the row pitch:
+//   * the staged row pitch Pp is chosen with Pp = -out_s1 (mod 8) and the first row starts k0 = (address / 4) mod 8
+//     floats in, so that a voxel's index in the stage buffer is congruent to its global float address mod 8: a
+//     16-byte aligned shared-memory read is a 16-byte aligned global store, and 8 of them in a row are one sector;
+//   * 64 threads drain one row: the 31 whole sectors inside the tile's 256 columns as 62 float4 (a warp instruction
+//     writes 512 contiguous bytes), the ragged ends (the sector a row shares with the neighbouring tile, 0..7 floats
+//     on either side) as scalars.  Same grid as the plain kernel, nothing computed twice;
+//   * two stage buffers alternate.  PIPE: no __syncthreads -- a "staged" and a "drained" mbarrier per buffer; a thread
+//     arrives on "staged" after its stores and computes the NEXT chunk's voxels before it waits, so the skew between
+//     the warps of a CTA is absorbed by a chunk of arithmetic instead of stalling at a barrier eight times per tile.
+// Arithmetic and results are those of deskew_tma_kernel, bit for bit.
+constexpr int kStagePitch = 272;     // floats reserved per staged row: the pitch in use is 264 + (0..7)
+
+__device__ __forceinline__ void mbar_wait_parity(uint64_t *bar, uint32_t parity) {
+    while (!mbar_try_wait_s(smem_u32(bar), parity)) {
+    }
+}
+
+template <typename T, int NAVG, bool PIPE>
+__global__ void __launch_bounds__(kTmaThreads, NAVG <= 2 ? 4 : 3)
+    deskew_tma_staged_kernel(const __grid_constant__ CUtensorMap tmap, const DeskewParams P) {
+    constexpr int EPC = Chunk<T>::kElems;   // output rows per stage
+    constexpr int TX = 8 * EPC;
+    constexpr int T2 = 256;
+    extern __shared__ uint8_t smem_dyn[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ __align__(8) uint64_t bar_staged[2], bar_drained[2];
+
+    const uint32_t pad = (1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u;
+    const uint8_t *tile = smem_dyn + pad;
+    const uint32_t region_bytes = (uint32_t)P.nz_cap * kRowBytes;
+    float *stage = reinterpret_cast<float *>(smem_dyn + pad + NAVG * region_bytes);   // 2 x EPC x kStagePitch floats
+
+    const int tx = blockIdx.x % P.tiles_x;
+    const int t2 = blockIdx.x / P.tiles_x;
+    const int p = P.p0 + blockIdx.y;
+    const int x0 = tx * TX;
+    const int c0 = P.cbeg + t2 * T2;
+    const int ncols = min(T2, P.cend - c0);   // columns of this tile that exist
+    const int c_last = c0 + ncols - 1;
+    const double zmax = (double)(P.Z - 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    __shared__ double s_base[NAVG];
+    __shared__ int s_zlo[NAVG];
+    __shared__ unsigned s_need;
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_init(&bar, 1);
+            if (PIPE) {
+                mbar_init(&bar_staged[0], kTmaThreads);
+                mbar_init(&bar_staged[1], kTmaThreads);
+                mbar_init(&bar_drained[0], kTmaThreads);
+                mbar_init(&bar_drained[1], kTmaThreads);
+            }
+            fence_mbar_init();
+        }
+        bool need = false;
+        int zlo = 0, yrow = 0;
+        if (lane < NAVG) {
+            const int o0 = min(NAVG * p + lane, P.Y - 1);
+            yrow = P.Y - 1 - o0 - P.y_org;
+            const double base = __dadd_rn(P.shift, __dmul_rn((double)o0, P.m00));
+            const double zfirst = scan_coord(base, c0, P.m02);
+            const double zlast = scan_coord(base, c_last, P.m02);
+            need = !(zlast < 0.0 || zfirst > zmax);
+            zlo = __double2int_rd(fmin(fmax(zfirst, 0.0), zmax));
+            s_base[lane] = base;
+            s_zlo[lane] = zlo;
+        }
+        const unsigned mask = __ballot_sync(0xffffffffu, need);
+        if (lane == 0) {
+            s_need = mask;
+            if (mask) mbar_arrive_expect_tx(&bar, (uint32_t)__popc(mask) * region_bytes);
+        }
+        __syncwarp();
+        if (need) tma_load_3d(smem_u32(tile) + lane * region_bytes, &tmap, x0, yrow, zlo - P.z_org, &bar);
+    }
+    __syncthreads();
+    const bool any_need = s_need != 0;
+
+    const int t_local = threadIdx.x;   // one thread = one column of the tile
+    const int o2 = c0 + t_local;
+    const bool col_ok = t_local < ncols;
+
+    float w[NAVG], u[NAVG];
+    uint32_t off0[NAVG], off1[NAVG], sw0[NAVG], sw1[NAVG];
+    bool inside[NAVG];
+#pragma unroll
+    for (int k = 0; k < NAVG; ++k) {
+        const int zlo = s_zlo[k];
+        const double z = scan_coord(s_base[k], o2, P.m02);
+        inside[k] = col_ok && z >= 0.0 && z <= zmax;
+        const int z0 = inside[k] ? __double2int_rd(z) : zlo;
+        w[k] = inside[k] ? (float)(z - (double)z0) : 0.f;
+        u[k] = w[k] * P.inv_n;
+        const int r0 = min(z0 - zlo, P.nz_cap - 1);
+        const int r1 = min(min(z0 + 1, P.Z - 1) - zlo, P.nz_cap - 1);
+        off0[k] = k * region_bytes + (uint32_t)r0 * kRowBytes;
+        off1[k] = k * region_bytes + (uint32_t)r1 * kRowBytes;
+        sw0[k] = ((uint32_t)r0 & 7u) << 4;
+        sw1[k] = ((uint32_t)r1 & 7u) << 4;
+    }
+
+    // stage geometry (uniform over the CTA): pitch and start offset that make stage index == global float address mod 8
+    const uint32_t s1m = (uint32_t)(P.out_s1 & 7);
+    const uint32_t pitch = 264u + ((8u - s1m) & 7u);
+    float *const row0 = P.out + (long long)(p - P.p0) * P.out_sp + (c0 - P.cbeg);   // (row o1 = 0, column c0)
+    const uint32_t a_first = (uint32_t)(reinterpret_cast<uintptr_t>(row0 + (long long)(P.X - 1 - x0) * P.out_s1) >> 2);
+
+    // drain role: row (threadIdx >> 6) of each pass of four rows, float4 number (threadIdx & 63) of that row
+    const int drow = threadIdx.x >> 6, dk = threadIdx.x & 63;
+
+    if (any_need) mbar_wait(&bar, 0);
+
+    bool all_in = true, none_in = true;
+#pragma unroll
+    for (int k = 0; k < NAVG; ++k) {
+        all_in &= inside[k];
+        none_in &= !inside[k];
+    }
+    const bool warp_all_in = __all_sync(0xffffffffu, all_in);
+    const bool warp_none_in = __all_sync(0xffffffffu, none_in);
+
+    auto compute = [&](int c, float *r) {
+        if (warp_all_in) {
+            Chunk<T>::template fast<NAVG>(tile, off0, off1, sw0, sw1, w, u, (uint32_t)c << 4, P.inv_n, r);
+        } else if (warp_none_in) {
+#pragma unroll
+            for (int j = 0; j < EPC; ++j) r[j] = P.cval;
+        } else {
+            float S[EPC], W[EPC], one[EPC];
+#pragma unroll
+            for (int k = 0; k < NAVG; ++k) {
+                uint4 A = make_uint4(0, 0, 0, 0), B = A;
+                if (inside[k]) {
+                    A = *reinterpret_cast<const uint4 *>(tile + off0[k] + (((uint32_t)c << 4) ^ sw0[k]));
+                    B = *reinterpret_cast<const uint4 *>(tile + off1[k] + (((uint32_t)c << 4) ^ sw1[k]));
+                }
+#pragma unroll
+                for (int j = 0; j < EPC; ++j) {
+                    const float a = inside[k] ? Chunk<T>::get(A, j) : P.cval;
+                    const float d = inside[k] ? Chunk<T>::get(B, j) - a : 0.f;
+                    S[j] = (k == 0) ? a : S[j] + a;
+                    W[j] = (k == 0) ? u[k] * d : fmaf(u[k], d, W[j]);
+                    if (k == 0) one[j] = fmaf(w[k], d, a);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < EPC; ++j) r[j] = none_in ? P.cval : (NAVG == 1) ? one[j] : fmaf(S[j], P.inv_n, W[j]);
+        }
+    };
+    // alignment of (row of chunk c, column c0): rows go DOWN in address as x goes up
+    auto k0_of = [&](int c) { return (a_first - (uint32_t)(c * EPC) * (uint32_t)P.out_s1) & 7u; };
+    auto stage_chunk = [&](int c, const float *r) {
+        if (col_ok) {
+            float *dst = stage + (c & 1) * (EPC * kStagePitch) + t_local + k0_of(c);
+#pragma unroll
+            for (int j = 0; j < EPC; ++j) {
+                *dst = r[j];
+                dst += pitch;
+            }
+        }
+    };
+    auto drain_chunk = [&](int c) {
+        const int xc = x0 + c * EPC;
+        const uint32_t k0 = k0_of(c);
+        const float *buf = stage + (c & 1) * (EPC * kStagePitch);
+#pragma unroll
+        for (int ps = 0; ps < EPC / 4; ++ps) {
+            const int j = ps * 4 + drow;
+            const int x = xc + j;
+            if (x >= P.X) continue;
+            const uint32_t s0 = (uint32_t)j * pitch + k0;    // stage index of the row's column c0
+            const int t_lo = (int)((8u - (s0 & 7u)) & 7u);     // first whole sector of the row inside the tile
+            const float *src = buf + s0;
+            float *grow = row0 + (long long)(P.X - 1 - x) * P.out_s1;
+            if (dk < 62) {
+                const int t = t_lo + 4 * dk;                  // 62 float4 = the 31 sectors that always lie inside
+                if (t + 3 < ncols) {
+                    const float4 v = *reinterpret_cast<const float4 *>(src + t);
+                    __stcs(reinterpret_cast<float4 *>(grow + t), v);
+                } else {
+                    for (int e = t; e < ncols; ++e) __stcs(grow + e, src[e]);   // the row ends inside this tile
+                }
+            } else if (dk == 62) {
+                for (int e = 0; e < min(t_lo, ncols); ++e) __stcs(grow + e, src[e]);            // ragged head
+            } else {
+                for (int e = t_lo + 248; e < ncols; ++e) __stcs(grow + e, src[e]);               // ragged tail
+            }
+        }
+    };
+
+    if (!PIPE) {
+        for (int c = 0; c < 8; ++c) {
+            float r[EPC];
+            compute(c, r);
+            stage_chunk(c, r);
+            __syncthreads();   // the chunk is staged; the buffer drained two chunks ago is free again after this barrier
+            drain_chunk(c);
+        }
+    } else {
+        float r[EPC];
+        compute(0, r);
+        stage_chunk(0, r);
+        mbar_arrive(&bar_staged[0]);
+        for (int c = 0; c < 8; ++c) {
+            float rn[EPC];
+            if (c + 1 < 8) compute(c + 1, rn);                         // arithmetic of the next chunk covers the skew
+            mbar_wait_parity(&bar_staged[c & 1], (uint32_t)(c >> 1) & 1u);
+            drain_chunk(c);
+            mbar_arrive(&bar_drained[c & 1]);
+            if (c + 1 < 8) {
+                if (c >= 1) mbar_wait_parity(&bar_drained[(c + 1) & 1], (uint32_t)((c - 1) >> 1) & 1u);   // chunk c-1 has left it
+                stage_chunk(c + 1, rn);
+                mbar_arrive(&bar_staged[(c + 1) & 1]);
+            }
+        }
+    }
+}
+
 __global__ void range_init_kernel(unsigned *slots) {
     slots[0] = 0xffffffffu;
     slots[1] = 0u;
@@ -551,6 +782,18 @@ static int launch_direct(const DeskewParams &Pin, cudaStream_t stream) {
 }
 
 template <typename T, int NAVG>
+static int launch_tma_staged_n(const CUtensorMap &tmap, const DeskewParams &P, size_t smem, cudaStream_t stream) {
+    static const bool pipe = env_int("SHRIMPY_DESKEW_STAGE_PIPE", 1) != 0;
+    auto kern = pipe ? deskew_tma_staged_kernel<T, NAVG, true> : deskew_tma_staged_kernel<T, NAVG, false>;
+    if (smem + 1024 > 48 * 1024)
+        SHRIMPY_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<dim3((unsigned)((long long)P.tiles_x * P.tiles_o2), (unsigned)P.pcount), kTmaThreads, smem, stream>>>(tmap, P);
+    count_launch();
+    SHRIMPY_CUDA_TRY(cudaGetLastError());
+    return SHRIMPY_OK;
+}
+
+template <typename T, int NAVG>
 static int launch_tma_n(const CUtensorMap &tmap, const DeskewParams &P, size_t smem, cudaStream_t stream, bool aligned) {
     auto kern = P.scale ? (P.range ? deskew_tma_kernel<T, NAVG, true, true> : deskew_tma_kernel<T, NAVG, true, false>)
                         : (P.range ? deskew_tma_kernel<T, NAVG, false, true> : deskew_tma_kernel<T, NAVG, false, false>);
@@ -566,7 +809,8 @@ static int launch_tma_n(const CUtensorMap &tmap, const DeskewParams &P, size_t s
 // Returns SHRIMPY_OK and sets *used = true when the TMA kernel was launched; *used = false
 // (still SHRIMPY_OK) when the problem is not eligible and the caller should fall back.
 template <typename T>
-static int launch_tma(const DeskewParams &Pin, cudaStream_t stream, bool *used, bool required, bool aligned = false) {
+static int launch_tma(const DeskewParams &Pin, cudaStream_t stream, bool *used, bool required, bool aligned = false,
+                      bool staged = false) {
     *used = false;
     DeskewParams P = Pin;
     constexpr int ES = (int)sizeof(T);
@@ -578,22 +822,24 @@ static int launch_tma(const DeskewParams &Pin, cudaStream_t stream, bool *used, 
     else if ((P.raw_sy * ES) % 16 != 0 || (P.raw_sz * ES) % 16 != 0) why = "raw strides not multiples of 16 bytes";
     else if (P.raw_sy < P.X || P.raw_sz < (long long)P.y_cnt * P.raw_sy) why = "raw strides overlap";
     else if (P.pcount > 65535) why = "too many tilt blocks for grid.y";
-    else if (aligned && (P.scale || P.range)) why = "whole-sector spans are not built for the fused scale / value range";
+    else if ((aligned || staged) && (P.scale || P.range)) why = "whole-sector spans are not built for the fused scale / value range";
 
     if (!why) {
         // Tile extent along o2: the staged scan range must fit nz_cap <= 256 slices and the CTA's
         // shared memory; default 128 columns, overridable for experiments.
         int T2 = env_int("SHRIMPY_DESKEW_T2", 256);
+        if (staged) T2 = 256;
         if (T2 != 32 && T2 != 64 && T2 != 128 && T2 != 256) T2 = 256;
         const int smem_budget = env_int("SHRIMPY_DESKEW_SMEM", 72 * 1024);
+        const long long stage_bytes = staged ? 2LL * (16 / ES) * kStagePitch * (long long)sizeof(float) : 0;
         for (;; T2 >>= 1) {
-            if (T2 < 32) {
+            if (T2 < 32 || (staged && T2 != 256)) {
                 why = "px_to_scan_ratio too large for a staged tile";
                 break;
             }
             const long long nz = (long long)std::ceil((T2 - 1) * P.m02) + 3;
             const long long cap = (nz + 7) / 8 * 8;
-            if (cap <= 256 && cap * kRowBytes * P.n + 1024 <= smem_budget) {
+            if (cap <= 256 && cap * kRowBytes * P.n + stage_bytes + 1024 <= smem_budget) {
                 P.T2 = T2;
                 P.nz_cap = (int)cap;
                 break;
@@ -605,7 +851,7 @@ static int launch_tma(const DeskewParams &Pin, cudaStream_t stream, bool *used, 
         return SHRIMPY_OK;
     }
     P.tiles_x = (P.X + TX - 1) / TX;
-    const int step2 = aligned ? P.T2 - 8 : P.T2;
+    const int step2 = aligned ? P.T2 - 8 : P.T2;     // the staged variant advances by whole tiles: its overlap columns belong to a ninth warp
     P.tiles_o2 = (P.cend - P.cbeg + step2 - 1) / step2;
     if ((long long)P.tiles_x * P.tiles_o2 > 2147483647LL) {
         if (required) return fail(SHRIMPY_EINVAL, "deskew: grid too large");
@@ -627,8 +873,19 @@ static int launch_tma(const DeskewParams &Pin, cudaStream_t stream, bool *used, 
         if (required) return fail(SHRIMPY_ECUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)rc);
         return SHRIMPY_OK;
     }
-    const size_t smem = (size_t)P.nz_cap * kRowBytes * P.n + 1024;
+    const size_t smem = (size_t)P.nz_cap * kRowBytes * P.n + 1024 +
+                        (staged ? 2u * (16 / ES) * kStagePitch * sizeof(float) : 0u);
     int err;
+    if (staged) {
+        switch (P.n) {
+            case 1: err = launch_tma_staged_n<T, 1>(tmap, P, smem, stream); break;
+            case 2: err = launch_tma_staged_n<T, 2>(tmap, P, smem, stream); break;
+            case 3: err = launch_tma_staged_n<T, 3>(tmap, P, smem, stream); break;
+            default: err = launch_tma_staged_n<T, 4>(tmap, P, smem, stream); break;
+        }
+        if (err == SHRIMPY_OK) *used = true;
+        return err;
+    }
     switch (P.n) {
         case 1: err = launch_tma_n<T, 1>(tmap, P, smem, stream, aligned); break;
         case 2: err = launch_tma_n<T, 2>(tmap, P, smem, stream, aligned); break;
@@ -643,8 +900,9 @@ template <typename T>
 static int deskew_dispatch(const DeskewParams &P, int kernel, cudaStream_t stream) {
     if (kernel != SHRIMPY_KERNEL_DIRECT) {
         bool used = false;
-        const bool forced = kernel == SHRIMPY_KERNEL_TMA_ALIGNED;
-        bool aligned = forced;
+        const bool forced = kernel == SHRIMPY_KERNEL_TMA_ALIGNED || kernel == SHRIMPY_KERNEL_TMA_STAGED;
+        bool aligned = kernel == SHRIMPY_KERNEL_TMA_ALIGNED;
+        const bool staged = kernel == SHRIMPY_KERNEL_TMA_STAGED;
         if (kernel == SHRIMPY_KERNEL_AUTO && !P.scale && !P.range && (P.out_s1 % 8) != 0) {
             // Measured on B200 (profiles/r02_aligned_rows_probe.json): into rows of an odd pitch the whole-sector
             // variant wins where the writes dominate -- n = 1: 0.829 -> 0.780 ms, keep_overhang 1.197 -> 1.114 ms,
@@ -653,7 +911,7 @@ static int deskew_dispatch(const DeskewParams &P, int kernel, cudaStream_t strea
             static const int pref = env_int("SHRIMPY_DESKEW_ALIGNED", 1);
             aligned = pref >= 2 || (pref == 1 && P.n == 1);
         }
-        const int err = launch_tma<T>(P, stream, &used, kernel == SHRIMPY_KERNEL_TMA || forced, aligned);
+        const int err = launch_tma<T>(P, stream, &used, kernel == SHRIMPY_KERNEL_TMA || forced, aligned, staged);
         if (err != SHRIMPY_OK || used) return err;
     }
     return launch_direct<T>(P, stream);
@@ -711,7 +969,7 @@ static int deskew_window_impl(const void *d_raw, int raw_dtype, float *d_out, in
         return fail(SHRIMPY_EINVAL, "deskew: bad shape Z=%d Y=%d X=%d Xp=%d n=%d", Z, Y, X, Xp, n_avg);
     if (raw_dtype != SHRIMPY_U16 && raw_dtype != SHRIMPY_F32)
         return fail(SHRIMPY_EINVAL, "deskew: raw_dtype must be SHRIMPY_U16 or SHRIMPY_F32, got %d", raw_dtype);
-    if (kernel < SHRIMPY_KERNEL_AUTO || kernel > SHRIMPY_KERNEL_TMA_ALIGNED)
+    if (kernel < SHRIMPY_KERNEL_AUTO || kernel > SHRIMPY_KERNEL_TMA_STAGED)
         return fail(SHRIMPY_EINVAL, "deskew: unknown kernel selector %d", kernel);
     if (!std::isfinite(m00) || !std::isfinite(m02) || !std::isfinite(shift))
         return fail(SHRIMPY_EINVAL, "deskew: non-finite affine row");
