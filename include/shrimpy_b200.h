@@ -53,12 +53,10 @@ enum {
     SHRIMPY_KERNEL_AUTO = 0,
     SHRIMPY_KERNEL_DIRECT = 1, /* plain gather, any shape/stride/alignment       */
     SHRIMPY_KERNEL_TMA = 2,    /* TMA-staged smem tiles, 128-bit smem reads      */
-    /* The TMA kernel with overlapping o2 tiles, each storing only whole 32-byte sectors of an output row (for contiguous
-     * results whose row length Xp is not a multiple of 8 floats).  Never chosen by AUTO; same voxels bit for bit. */
-    SHRIMPY_KERNEL_TMA_ALIGNED = 3,
     /* The TMA kernel with its results staged through shared memory and stored as 16-byte vectors on 32-byte
-     * boundaries whatever the row pitch (csrc/deskew.cu deskew_tma_staged_kernel); same voxels bit for bit. */
-    SHRIMPY_KERNEL_TMA_STAGED = 4
+     * boundaries whatever the row pitch (csrc/deskew.cu deskew_tma_staged_kernel); same voxels bit for bit.  AUTO takes
+     * it for average_n_slices == 1, where the writes dominate. */
+    SHRIMPY_KERNEL_TMA_STAGED = 3
 };
 
 int shrimpy_abi_version(void);

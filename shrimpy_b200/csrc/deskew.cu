@@ -291,14 +291,7 @@ constexpr int kMaxTmaAvg = 4;   // template instantiations exist for n = 1..4
 // one atomicMin / atomicMax pair per CTA on ordered keys): the min/max pass the tracking step makes right after
 // the deskew (shrimpy/dynatrack/tracking.py:583-584) disappears.
 //
-// ALIGNED (opt-in, SHRIMPY_KERNEL_TMA_ALIGNED): whole-sector row spans for contiguous outputs whose row length is not a
-// multiple of 8 floats.  Tiles advance by T2 - 8 columns while the 256 threads still cover T2, so neighbouring tiles
-// overlap by 8 columns; every 32-byte sector of an output row is stored by exactly ONE tile -- the tile that holds the
-// column of the sector's first float (clamped to the window's first column) -- and the overlap voxels are computed
-// twice but stored once.  Only the first and last warp of a tile's o2 span ever skip a store; their test is three
-// integer instructions on the store address.  `tools/sector_spans.py` mirrors the rule and `tests/test_sector_spans.py`
-// proves on the CPU that every voxel has exactly one owner.
-template <typename T, int NAVG, bool SCALED, bool RANGE, bool ALIGNED = false>
+template <typename T, int NAVG, bool SCALED, bool RANGE>
 __global__ void __launch_bounds__(kTmaThreads, 4)
     deskew_tma_kernel(const __grid_constant__ CUtensorMap tmap, const DeskewParams P) {
     constexpr int EPC = Chunk<T>::kElems;
@@ -319,8 +312,7 @@ __global__ void __launch_bounds__(kTmaThreads, 4)
     const int t2 = blockIdx.x / P.tiles_x;
     const int p = P.p0 + blockIdx.y;
     const int x0 = tx * TX;
-    const int step2 = ALIGNED ? P.T2 - 8 : P.T2;   // columns between the first columns of neighbouring tiles
-    const int c0 = P.cbeg + t2 * step2;
+    const int c0 = P.cbeg + t2 * P.T2;
     const int c_last = min(c0 + P.T2, P.cend) - 1;
     const double zmax = (double)(P.Z - 1);
 
@@ -411,14 +403,6 @@ __global__ void __launch_bounds__(kTmaThreads, 4)
     const long long row_bytes = P.out_s1 * (long long)sizeof(float);
     float vlo = 3.402823466e38f, vhi = -3.402823466e38f;
 
-    // ALIGNED: a = (address / 4) & 7 is the voxel's place inside its sector, t - a the tile-local column of the
-    // sector's first float.  The tile owns the sector iff 0 <= t - a < step2 (tile 0 also owns t - a < 0):
-    // store iff own_lo < a <= own_hi.  Only threads with t < 8 or t >= step2 can fail the test.
-    const int t_local = (warp % warps_o2) * 32 + lane;
-    const int own_hi = (!ALIGNED || t2 == 0) ? 7 : min(t_local, 7);
-    const int own_lo = ALIGNED ? t_local - step2 : -1;
-    const bool edge_warp = ALIGNED && ((warp % warps_o2) == 0 || (warp % warps_o2) == warps_o2 - 1);
-
     for (int c = part; c < 8; c += parts) {
         float r[EPC];
         if (warp_all_in) {
@@ -459,14 +443,7 @@ __global__ void __launch_bounds__(kTmaThreads, 4)
             const int xc = x0 + c * EPC;
             const int xvalid = P.X - xc;  // elements of this chunk that exist (uniform over the CTA)
             char *ptr = out_col + (long long)(P.X - 1 - xc) * row_bytes;
-            if (ALIGNED && (edge_warp || xvalid < EPC)) {
-#pragma unroll
-                for (int j = 0; j < EPC; ++j) {
-                    const int a = (int)((reinterpret_cast<uintptr_t>(ptr) >> 2) & 7u);
-                    if (j < xvalid && a > own_lo && a <= own_hi) __stcs(reinterpret_cast<float *>(ptr), r[j]);
-                    ptr -= row_bytes;
-                }
-            } else if (xvalid >= EPC) {
+            if (xvalid >= EPC) {
 #pragma unroll
                 for (int j = 0; j < EPC; ++j) {
                     __stcs(reinterpret_cast<float *>(ptr), r[j]);   // streaming: outputs are never re-read
@@ -524,8 +501,8 @@ __global__ void __launch_bounds__(kTmaThreads, 4)
 // When a row is not a whole number of 32-byte sectors long (Xp = 1279, 1799, 10517: every mantis geometry), every row
 // starts at another offset inside a sector, each of those 128-byte warp stores straddles sector boundaries, and the
 // write-dominated deskews lose a quarter of their bandwidth to partial-sector writes (measured: the same launch into
-// rows padded to whole sectors runs 0.83 -> 0.64 ms; overlapping the tiles so that tile edges fall on sector
-// boundaries -- ALIGNED above -- recovers only 6 % of it, because the seven warp boundaries inside a tile stay ragged).
+// rows padded to whole sectors runs 0.83 -> 0.64 ms; a variant of this kernel with overlapping tiles whose edges fell
+// on sector boundaries recovered only 6 % of it, because the seven warp boundaries inside a tile stayed ragged).
 //
 // Here a chunk's results (EPC output rows x 256 columns) go through shared memory and leave as 16-byte stores that
 // start on 32-byte boundaries of global memory, whatever the row pitch:
@@ -535,18 +512,12 @@ __global__ void __launch_bounds__(kTmaThreads, 4)
 //   * 64 threads drain one row: the 31 whole sectors inside the tile's 256 columns as 62 float4 (a warp instruction
 //     writes 512 contiguous bytes), the ragged ends (the sector a row shares with the neighbouring tile, 0..7 floats
 //     on either side) as scalars.  Same grid as the plain kernel, nothing computed twice;
-//   * two stage buffers alternate.  PIPE: no __syncthreads -- a "staged" and a "drained" mbarrier per buffer; a thread
-//     arrives on "staged" after its stores and computes the NEXT chunk's voxels before it waits, so the skew between
-//     the warps of a CTA is absorbed by a chunk of arithmetic instead of stalling at a barrier eight times per tile.
+//   * two stage buffers alternate, one __syncthreads per chunk (a split arrive / wait pair of mbarriers per buffer with
+//     the next chunk's arithmetic in between was tried and measured 5-15 % slower).
 // Arithmetic and results are those of deskew_tma_kernel, bit for bit.
 constexpr int kStagePitch = 272;     // floats reserved per staged row: the pitch in use is 264 + (0..7)
 
-__device__ __forceinline__ void mbar_wait_parity(uint64_t *bar, uint32_t parity) {
-    while (!mbar_try_wait_s(smem_u32(bar), parity)) {
-    }
-}
-
-template <typename T, int NAVG, bool PIPE>
+template <typename T, int NAVG>
 __global__ void __launch_bounds__(kTmaThreads, NAVG <= 2 ? 4 : 3)
     deskew_tma_staged_kernel(const __grid_constant__ CUtensorMap tmap, const DeskewParams P) {
     constexpr int EPC = Chunk<T>::kElems;   // output rows per stage
@@ -554,7 +525,6 @@ __global__ void __launch_bounds__(kTmaThreads, NAVG <= 2 ? 4 : 3)
     constexpr int T2 = 256;
     extern __shared__ uint8_t smem_dyn[];
     __shared__ __align__(8) uint64_t bar;
-    __shared__ __align__(8) uint64_t bar_staged[2], bar_drained[2];
 
     const uint32_t pad = (1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u;
     const uint8_t *tile = smem_dyn + pad;
@@ -577,12 +547,6 @@ __global__ void __launch_bounds__(kTmaThreads, NAVG <= 2 ? 4 : 3)
     if (warp == 0) {
         if (lane == 0) {
             mbar_init(&bar, 1);
-            if (PIPE) {
-                mbar_init(&bar_staged[0], kTmaThreads);
-                mbar_init(&bar_staged[1], kTmaThreads);
-                mbar_init(&bar_drained[0], kTmaThreads);
-                mbar_init(&bar_drained[1], kTmaThreads);
-            }
             fence_mbar_init();
         }
         bool need = false;
@@ -638,8 +602,37 @@ __global__ void __launch_bounds__(kTmaThreads, NAVG <= 2 ? 4 : 3)
     float *const row0 = P.out + (long long)(p - P.p0) * P.out_sp + (c0 - P.cbeg);   // (row o1 = 0, column c0)
     const uint32_t a_first = (uint32_t)(reinterpret_cast<uintptr_t>(row0 + (long long)(P.X - 1 - x0) * P.out_s1) >> 2);
 
-    // drain role: row (threadIdx >> 6) of each pass of four rows, float4 number (threadIdx & 63) of that row
+    // drain role: row (threadIdx >> 6) of each pass of four rows, float4 number (threadIdx & 63) of that row.  What a
+    // thread stores is the same in every chunk (a chunk is EPC rows: the alignment pattern repeats every 8 rows, and
+    // for EPC = 4 it alternates between two patterns), so offsets and predicates are set up once, per pass and parity.
     const int drow = threadIdx.x >> 6, dk = threadIdx.x & 63;
+    constexpr int PASSES = EPC / 4, PAR = EPC == 8 ? 1 : 2;
+    uint32_t d_src[PAR][PASSES];      // byte offset of this thread's float4 inside a stage buffer
+    int d_col[PAR][PASSES];           // its first column (local); < 0: no float4 for this thread
+    int d_rag[PAR][PASSES];           // local column of its ragged-end scalar; < 0: none
+    uint32_t d_s0[PAR][PASSES];       // stage index of the row's column c0
+#pragma unroll
+    for (int par = 0; par < PAR; ++par) {
+        const uint32_t k0 = (a_first - (uint32_t)(par * EPC) * (uint32_t)P.out_s1) & 7u;
+#pragma unroll
+        for (int ps = 0; ps < PASSES; ++ps) {
+            const int j = ps * 4 + drow;
+            const uint32_t s0 = (uint32_t)j * pitch + k0;
+            const int t_lo = (int)((8u - (s0 & 7u)) & 7u);      // first whole sector of the row inside the tile
+            const int t = t_lo + 4 * dk;                          // 62 float4 = the 31 sectors that always lie inside
+            d_s0[par][ps] = s0;
+            d_src[par][ps] = (s0 + (uint32_t)t) * 4u;
+            d_col[par][ps] = (dk < 62 && t + 3 < ncols) ? t : -1;
+            // ragged ends, one scalar per thread: the head [0, t_lo) by threads 0..6, the tail [t_lo + 248, 256) by
+            // threads 8..15, and where the row ends inside the tile its last 1..3 floats by threads 16..18
+            const int body_end = t_lo + 4 * min(62, max(0, (ncols - t_lo) >> 2));
+            const int e = dk < 8 ? dk : dk < 16 ? t_lo + 248 + (dk - 8) : body_end + (dk - 16);
+            const bool ragged = dk < 8 ? dk < min(t_lo, ncols) : dk < 16 ? e < ncols : (dk < 19 && body_end < t_lo + 248 && e < ncols);
+            d_rag[par][ps] = ragged ? e : -1;
+        }
+    }
+    // running global pointer of (this thread's drain row of the current chunk, column c0)
+    float *d_row = row0 + (long long)(P.X - 1 - x0 - drow) * P.out_s1;
 
     if (any_need) mbar_wait(&bar, 0);
 
@@ -694,58 +687,32 @@ __global__ void __launch_bounds__(kTmaThreads, NAVG <= 2 ? 4 : 3)
     };
     auto drain_chunk = [&](int c) {
         const int xc = x0 + c * EPC;
-        const uint32_t k0 = k0_of(c);
-        const float *buf = stage + (c & 1) * (EPC * kStagePitch);
+        const int par = EPC == 8 ? 0 : (c & 1);
+        const char *buf = reinterpret_cast<const char *>(stage + (c & 1) * (EPC * kStagePitch));
 #pragma unroll
-        for (int ps = 0; ps < EPC / 4; ++ps) {
-            const int j = ps * 4 + drow;
-            const int x = xc + j;
-            if (x >= P.X) continue;
-            const uint32_t s0 = (uint32_t)j * pitch + k0;    // stage index of the row's column c0
-            const int t_lo = (int)((8u - (s0 & 7u)) & 7u);     // first whole sector of the row inside the tile
-            const float *src = buf + s0;
-            float *grow = row0 + (long long)(P.X - 1 - x) * P.out_s1;
-            if (dk < 62) {
-                const int t = t_lo + 4 * dk;                  // 62 float4 = the 31 sectors that always lie inside
-                if (t + 3 < ncols) {
-                    const float4 v = *reinterpret_cast<const float4 *>(src + t);
+        for (int ps = 0; ps < PASSES; ++ps) {
+            float *grow = d_row - (long long)(ps * 4) * P.out_s1;
+            if (xc + ps * 4 + drow < P.X) {
+                const int t = PAR == 1 ? d_col[0][ps] : d_col[par][ps];
+                if (t >= 0) {
+                    const float4 v = *reinterpret_cast<const float4 *>(buf + (PAR == 1 ? d_src[0][ps] : d_src[par][ps]));
                     __stcs(reinterpret_cast<float4 *>(grow + t), v);
-                } else {
-                    for (int e = t; e < ncols; ++e) __stcs(grow + e, src[e]);   // the row ends inside this tile
                 }
-            } else if (dk == 62) {
-                for (int e = 0; e < min(t_lo, ncols); ++e) __stcs(grow + e, src[e]);            // ragged head
-            } else {
-                for (int e = t_lo + 248; e < ncols; ++e) __stcs(grow + e, src[e]);               // ragged tail
+                if (dk < 19) {           // the first warp of a row also carries its ragged ends
+                    const int e = PAR == 1 ? d_rag[0][ps] : d_rag[par][ps];
+                    if (e >= 0) __stcs(grow + e, reinterpret_cast<const float *>(buf)[(PAR == 1 ? d_s0[0][ps] : d_s0[par][ps]) + e]);
+                }
             }
         }
+        d_row -= (long long)EPC * P.out_s1;
     };
 
-    if (!PIPE) {
-        for (int c = 0; c < 8; ++c) {
-            float r[EPC];
-            compute(c, r);
-            stage_chunk(c, r);
-            __syncthreads();   // the chunk is staged; the buffer drained two chunks ago is free again after this barrier
-            drain_chunk(c);
-        }
-    } else {
+    for (int c = 0; c < 8; ++c) {
         float r[EPC];
-        compute(0, r);
-        stage_chunk(0, r);
-        mbar_arrive(&bar_staged[0]);
-        for (int c = 0; c < 8; ++c) {
-            float rn[EPC];
-            if (c + 1 < 8) compute(c + 1, rn);                         // arithmetic of the next chunk covers the skew
-            mbar_wait_parity(&bar_staged[c & 1], (uint32_t)(c >> 1) & 1u);
-            drain_chunk(c);
-            mbar_arrive(&bar_drained[c & 1]);
-            if (c + 1 < 8) {
-                if (c >= 1) mbar_wait_parity(&bar_drained[(c + 1) & 1], (uint32_t)((c - 1) >> 1) & 1u);   // chunk c-1 has left it
-                stage_chunk(c + 1, rn);
-                mbar_arrive(&bar_staged[(c + 1) & 1]);
-            }
-        }
+        compute(c, r);
+        stage_chunk(c, r);
+        __syncthreads();   // the chunk is staged; the buffer drained two chunks ago is free again after this barrier
+        drain_chunk(c);
     }
 }
 
@@ -783,8 +750,7 @@ static int launch_direct(const DeskewParams &Pin, cudaStream_t stream) {
 
 template <typename T, int NAVG>
 static int launch_tma_staged_n(const CUtensorMap &tmap, const DeskewParams &P, size_t smem, cudaStream_t stream) {
-    static const bool pipe = env_int("SHRIMPY_DESKEW_STAGE_PIPE", 1) != 0;
-    auto kern = pipe ? deskew_tma_staged_kernel<T, NAVG, true> : deskew_tma_staged_kernel<T, NAVG, false>;
+    auto kern = deskew_tma_staged_kernel<T, NAVG>;
     if (smem + 1024 > 48 * 1024)
         SHRIMPY_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<dim3((unsigned)((long long)P.tiles_x * P.tiles_o2), (unsigned)P.pcount), kTmaThreads, smem, stream>>>(tmap, P);
@@ -794,10 +760,9 @@ static int launch_tma_staged_n(const CUtensorMap &tmap, const DeskewParams &P, s
 }
 
 template <typename T, int NAVG>
-static int launch_tma_n(const CUtensorMap &tmap, const DeskewParams &P, size_t smem, cudaStream_t stream, bool aligned) {
+static int launch_tma_n(const CUtensorMap &tmap, const DeskewParams &P, size_t smem, cudaStream_t stream) {
     auto kern = P.scale ? (P.range ? deskew_tma_kernel<T, NAVG, true, true> : deskew_tma_kernel<T, NAVG, true, false>)
                         : (P.range ? deskew_tma_kernel<T, NAVG, false, true> : deskew_tma_kernel<T, NAVG, false, false>);
-    if (aligned) kern = deskew_tma_kernel<T, NAVG, false, false, true>;   // launch_tma admits it without scale / range only
     if (smem + 1024 > 48 * 1024)  // static smem counts against the 48 KB default as well
         SHRIMPY_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<dim3((unsigned)((long long)P.tiles_x * P.tiles_o2), (unsigned)P.pcount), kTmaThreads, smem, stream>>>(tmap, P);
@@ -809,8 +774,7 @@ static int launch_tma_n(const CUtensorMap &tmap, const DeskewParams &P, size_t s
 // Returns SHRIMPY_OK and sets *used = true when the TMA kernel was launched; *used = false
 // (still SHRIMPY_OK) when the problem is not eligible and the caller should fall back.
 template <typename T>
-static int launch_tma(const DeskewParams &Pin, cudaStream_t stream, bool *used, bool required, bool aligned = false,
-                      bool staged = false) {
+static int launch_tma(const DeskewParams &Pin, cudaStream_t stream, bool *used, bool required, bool staged = false) {
     *used = false;
     DeskewParams P = Pin;
     constexpr int ES = (int)sizeof(T);
@@ -822,7 +786,7 @@ static int launch_tma(const DeskewParams &Pin, cudaStream_t stream, bool *used, 
     else if ((P.raw_sy * ES) % 16 != 0 || (P.raw_sz * ES) % 16 != 0) why = "raw strides not multiples of 16 bytes";
     else if (P.raw_sy < P.X || P.raw_sz < (long long)P.y_cnt * P.raw_sy) why = "raw strides overlap";
     else if (P.pcount > 65535) why = "too many tilt blocks for grid.y";
-    else if ((aligned || staged) && (P.scale || P.range)) why = "whole-sector spans are not built for the fused scale / value range";
+    else if (staged && (P.scale || P.range)) why = "the staged variant is not built for the fused scale / value range";
 
     if (!why) {
         // Tile extent along o2: the staged scan range must fit nz_cap <= 256 slices and the CTA's
@@ -851,8 +815,7 @@ static int launch_tma(const DeskewParams &Pin, cudaStream_t stream, bool *used, 
         return SHRIMPY_OK;
     }
     P.tiles_x = (P.X + TX - 1) / TX;
-    const int step2 = aligned ? P.T2 - 8 : P.T2;     // the staged variant advances by whole tiles: its overlap columns belong to a ninth warp
-    P.tiles_o2 = (P.cend - P.cbeg + step2 - 1) / step2;
+    P.tiles_o2 = (P.cend - P.cbeg + P.T2 - 1) / P.T2;
     if ((long long)P.tiles_x * P.tiles_o2 > 2147483647LL) {
         if (required) return fail(SHRIMPY_EINVAL, "deskew: grid too large");
         return SHRIMPY_OK;
@@ -887,10 +850,10 @@ static int launch_tma(const DeskewParams &Pin, cudaStream_t stream, bool *used, 
         return err;
     }
     switch (P.n) {
-        case 1: err = launch_tma_n<T, 1>(tmap, P, smem, stream, aligned); break;
-        case 2: err = launch_tma_n<T, 2>(tmap, P, smem, stream, aligned); break;
-        case 3: err = launch_tma_n<T, 3>(tmap, P, smem, stream, aligned); break;
-        default: err = launch_tma_n<T, 4>(tmap, P, smem, stream, aligned); break;
+        case 1: err = launch_tma_n<T, 1>(tmap, P, smem, stream); break;
+        case 2: err = launch_tma_n<T, 2>(tmap, P, smem, stream); break;
+        case 3: err = launch_tma_n<T, 3>(tmap, P, smem, stream); break;
+        default: err = launch_tma_n<T, 4>(tmap, P, smem, stream); break;
     }
     if (err == SHRIMPY_OK) *used = true;
     return err;
@@ -900,18 +863,15 @@ template <typename T>
 static int deskew_dispatch(const DeskewParams &P, int kernel, cudaStream_t stream) {
     if (kernel != SHRIMPY_KERNEL_DIRECT) {
         bool used = false;
-        const bool forced = kernel == SHRIMPY_KERNEL_TMA_ALIGNED || kernel == SHRIMPY_KERNEL_TMA_STAGED;
-        bool aligned = kernel == SHRIMPY_KERNEL_TMA_ALIGNED;
-        const bool staged = kernel == SHRIMPY_KERNEL_TMA_STAGED;
-        if (kernel == SHRIMPY_KERNEL_AUTO && !P.scale && !P.range && (P.out_s1 % 8) != 0) {
-            // Measured on B200 (profiles/r02_aligned_rows_probe.json): into rows of an odd pitch the whole-sector
-            // variant wins where the writes dominate -- n = 1: 0.829 -> 0.780 ms, keep_overhang 1.197 -> 1.114 ms,
-            // config 5 7.17 -> 6.85 ms -- and loses 14-18 % for n >= 2 (a sixth tile per 1279-column row costs more than
-            // the partial sectors).  AUTO therefore takes it for n == 1 only; SHRIMPY_DESKEW_ALIGNED=0 / 2 = never / always.
-            static const int pref = env_int("SHRIMPY_DESKEW_ALIGNED", 1);
-            aligned = pref >= 2 || (pref == 1 && P.n == 1);
-        }
-        const int err = launch_tma<T>(P, stream, &used, kernel == SHRIMPY_KERNEL_TMA || forced, aligned, staged);
+        const bool forced = kernel == SHRIMPY_KERNEL_TMA_STAGED;
+        // Measured on B200 (profiles/r02_staged_rows_probe.json): the staged variant wins wherever the writes dominate --
+        // n = 1: 0.82 -> 0.60 ms, keep_overhang 1.19 -> 0.84 ms, config 5 7.13 -> 5.18 ms (0.92 of the HBM peak), and still
+        // 3 % into rows of a whole-sector pitch -- and loses 3-17 % for n >= 2, where the plain kernel stays.
+        bool staged = forced || (kernel == SHRIMPY_KERNEL_AUTO && P.n == 1 && !P.scale && !P.range &&
+                                 env_int("SHRIMPY_DESKEW_STAGED", 1) != 0);
+        int err = launch_tma<T>(P, stream, &used, kernel == SHRIMPY_KERNEL_TMA || forced, staged);
+        if (err == SHRIMPY_OK && !used && staged && !forced)      // a 256-column tile does not fit (large r): plain tiles
+            err = launch_tma<T>(P, stream, &used, false, false);
         if (err != SHRIMPY_OK || used) return err;
     }
     return launch_direct<T>(P, stream);

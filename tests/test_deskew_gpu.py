@@ -273,18 +273,51 @@ def test_padded_row_output_is_the_same_volume(torch, sb, n, keep, kernel):
         sb.deskew_zyx(raw, 30.0, 0.39, keep, n, out=out, value_range=torch.empty(2, device="cuda"))
 
 
+@pytest.mark.parametrize("dtype", [np.uint16, np.float32])
 @pytest.mark.parametrize("shape,r,keep,n", [((90, 13, 128), 0.39, False, 1), ((120, 31, 200), 0.39, True, 3),
-                                            ((120, 31, 200), 0.651, False, 4), ((300, 40, 264), 1.3, True, 1)])
-def test_whole_sector_spans_variant_is_the_same_volume(torch, sb, shape, r, keep, n):
-    """``SHRIMPY_KERNEL_TMA_ALIGNED``: overlapping o2 tiles, every 32-byte sector of a row stored by one tile
-    (rule proven on the host mirror in tests/test_sector_spans.py).  Same voxels, nothing else touched."""
-    raw = torch.from_numpy(synthetic_stack(shape, seed=6)).cuda()
+                                            ((260, 11, 2048), 0.39, True, 1), ((64, 7, 72), 0.77, False, 2),
+                                            ((600, 10, 264), 0.39, False, 1)])
+def test_staged_variant_is_the_same_volume(torch, sb, shape, r, keep, n, dtype):
+    """``SHRIMPY_KERNEL_TMA_STAGED`` (what AUTO runs for average_n_slices == 1): results staged through shared memory
+    and stored as 16-byte vectors on 32-byte boundaries, ragged ends as scalars.  Same voxels as the plain kernel bit for
+    bit -- into a contiguous result of odd pitch, into padded rows, and into windows that start inside a sector -- and
+    nothing outside the target is touched."""
+    raw = torch.from_numpy(synthetic_stack(shape, seed=6, dtype=dtype)).cuda()
     want = sb.deskew_zyx(raw, 30.0, r, keep, n, kernel="tma")
     got = torch.full_like(want, -7.0)
-    sb.deskew_zyx(raw, 30.0, r, keep, n, out=got, kernel="tma_aligned")
+    sb.deskew_zyx(raw, 30.0, r, keep, n, out=got, kernel="tma_staged")
     assert torch.equal(got, want)
+    if n == 1:
+        assert torch.equal(sb.deskew_zyx(raw, 30.0, r, keep, n), want)          # AUTO
+    g = sb.deskew_geometry(shape, 30.0, r, keep, n)
+    P, X, Xp = g.out_shape
+    padded = sb.empty_deskewed(g, raw.device)
+    storage = padded.as_strided((P, X, padded.stride(1)), padded.stride())
+    storage.fill_(-7.0)
+    sb.deskew_zyx(raw, 30.0, r, keep, n, out=padded, kernel="tma_staged")
+    assert torch.equal(padded, want) and bool((storage[:, :, Xp:] == -7.0).all())
+    canvas = torch.full((P, X, Xp), -7.0, device="cuda")
+    for c0, c1 in ((3, min(Xp, 3 + 61)), (Xp // 3 + 1, Xp - 2), (5, min(Xp, 5 + 256 + 9))):
+        if c1 <= c0:
+            continue
+        _, zr = sb.window_needs(g, 0, P, c0, c1 - c0)
+        z0, z1 = (int(zr[0]), int(zr[1])) if zr[1] > zr[0] else (0, 1)
+        sb.deskew_window(raw[z0:z1], g, p_begin=0, p_count=P, c_begin=c0, c_count=c1 - c0, y_origin=0, z_origin=z0,
+                         out=canvas[:, :, c0:c1], kernel="tma_staged")
+        assert torch.equal(canvas[:, :, c0:c1], want[:, :, c0:c1])
+        canvas[:, :, c0:c1] = -7.0
+        assert bool((canvas == -7.0).all())
     with pytest.raises(Exception):
-        sb.deskew_zyx(raw, 30.0, r, keep, n, kernel="tma_aligned", value_range=torch.empty(2, device="cuda"))
+        sb.deskew_zyx(raw, 30.0, r, keep, n, kernel="tma_staged", value_range=torch.empty(2, device="cuda"))
+
+
+def test_staged_variant_refuses_what_does_not_fit_and_auto_falls_back(torch, sb):
+    from shrimpy_b200._cabi import ShrimpyB200Error
+
+    raw = torch.from_numpy(synthetic_stack((300, 12, 264), seed=8)).cuda()
+    with pytest.raises(ShrimpyB200Error):
+        sb.deskew_zyx(raw, 30.0, 1.3, True, 1, kernel="tma_staged")      # a 256-column tile spans > 256 scan slices
+    assert torch.equal(sb.deskew_zyx(raw, 30.0, 1.3, True, 1), sb.deskew_zyx(raw, 30.0, 1.3, True, 1, kernel="direct"))
 
 
 def test_broadcast_and_odd_stride_views_are_compacted_not_misread(torch, sb, oracle):

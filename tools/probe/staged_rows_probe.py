@@ -1,9 +1,9 @@
-"""Whole-sector stores into the CONTIGUOUS result -- ``kernel="tma_aligned"`` (overlapping tiles, csrc/deskew.cu ALIGNED)
-and ``kernel="tma_staged"`` (results staged through shared memory, 16-byte stores on sector boundaries) -- against the
-plain TMA kernel: first bit equality on awkward shapes (windows that start inside a sector, ragged X tiles, padded rows,
-every n, both dtypes), then the config-2 / n=1 / config-5 timings next to the same launches into padded rows.
+"""Whole-sector stores into the CONTIGUOUS result -- ``kernel="tma_staged"`` (results staged through shared memory,
+16-byte stores on sector boundaries, csrc/deskew.cu) -- against the plain TMA kernel: first bit equality on awkward
+shapes (windows that start inside a sector, ragged X tiles, padded rows, every n, both dtypes), then the config-2 /
+n=1 / config-5 timings next to the same launches into padded rows.
 
-    python tools/probe/aligned_rows_probe.py > gpurun_out/aligned_rows_probe.json
+    python tools/probe/staged_rows_probe.py > gpurun_out/staged_rows_probe.json
 """
 import json
 import sys
@@ -16,7 +16,7 @@ import shrimpy_b200 as sb
 from shrimpy_b200._cabi import ShrimpyB200Error
 
 res = {"equal": {}, "ms": {}}
-VARIANTS = ("tma_aligned", "tma_staged")
+VARIANTS = ("tma_staged",)
 gen = torch.Generator(device="cuda").manual_seed(7)
 
 
