@@ -402,7 +402,8 @@ class PagedStack(PagedWindow):
         self._fds = []
 
 
-def deskew_paged_split(stack, g: DeskewGeometry, shard: PagedShard, *, cval: float = 0.0, window_fn=None):
+def deskew_paged_split(stack, g: DeskewGeometry, shard: PagedShard, *, cval: float = 0.0, window_fn=None,
+                       kernel: str = "auto_columns_outermost"):
     """This rank's output columns ``out[:, :, c0:c1]`` in ONE launch over its window of the paged stack.
 
     ``stack`` needs ``slices(z0, z1)`` (``PagedStack``, or a host stand-in in the CPU tests); ``window_fn`` defaults
@@ -413,8 +414,10 @@ def deskew_paged_split(stack, g: DeskewGeometry, shard: PagedShard, *, cval: flo
         from .deskew import deskew_window
 
         def window_fn(slab, g, p_begin, p_count, c_begin, c_count, y_origin, z_origin, cval):
+            # column tiles outermost: the tiles that read the neighbour's pages (the window's first columns) are all
+            # in flight together at the start of the launch, so NVLink runs at its bandwidth, not at its latency
             return deskew_window(slab, g, p_begin=p_begin, p_count=p_count, c_begin=c_begin, c_count=c_count,
-                                 y_origin=y_origin, z_origin=z_origin, cval=cval)
+                                 y_origin=y_origin, z_origin=z_origin, cval=cval, kernel=kernel)
 
     Yn, X, _ = g.out_shape
     c0, c1 = shard.cols
