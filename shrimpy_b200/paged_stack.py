@@ -419,6 +419,9 @@ def deskew_paged_split(stack, g: DeskewGeometry, shard: PagedShard, *, cval: flo
             return deskew_window(slab, g, p_begin=p_begin, p_count=p_count, c_begin=c_begin, c_count=c_count,
                                  y_origin=y_origin, z_origin=z_origin, cval=cval, kernel=kernel)
 
+    # (Dispatching the column tiles outermost, so that every tile that reads remote pages is in flight at the start of
+    # the launch, was tried on 2 GPUs: 2.56 -> 4.54 ms -- the output writes lose their locality -- and removed;
+    # profiles/r02_scan_split_n2_with_block_order_experiment.json.)
     Yn, X, _ = g.out_shape
     c0, c1 = shard.cols
     z0, z1 = shard.need_z
