@@ -56,12 +56,7 @@ enum {
     /* The TMA kernel with its results staged through shared memory and stored as 16-byte vectors on 32-byte
      * boundaries whatever the row pitch (csrc/deskew.cu deskew_tma_staged_kernel); same voxels bit for bit.  AUTO takes
      * it for average_n_slices == 1, where the writes dominate. */
-    SHRIMPY_KERNEL_TMA_STAGED = 3,
-    /* Flag, OR-ed into a selector: dispatch the column (o2) tiles outermost -- every tilt block of the window's first
-     * columns before any of the next -- instead of innermost.  For slabs whose first columns read a neighbour GPU's
-     * pages over NVLink (paged_stack.py): all the remote tile loads are then in flight together at the start of the
-     * launch instead of ~5 % of the resident CTAs at any time, which is what bounds a latency-limited link. */
-    SHRIMPY_KERNEL_COLUMNS_OUTERMOST = 0x100
+    SHRIMPY_KERNEL_TMA_STAGED = 3
 };
 
 int shrimpy_abi_version(void);

@@ -17,11 +17,7 @@ LIB_PATH = LIB_DIR / "libshrimpy_b200.so"
 OK, EINVAL, ECUDA, ENOGPU, ENOMEM = range(5)
 U16, F32 = 0, 1
 KERNEL_AUTO, KERNEL_DIRECT, KERNEL_TMA, KERNEL_TMA_STAGED = 0, 1, 2, 3
-KERNEL_COLUMNS_OUTERMOST = 0x100
-KERNELS = {"auto": KERNEL_AUTO, "direct": KERNEL_DIRECT, "tma": KERNEL_TMA, "tma_staged": KERNEL_TMA_STAGED,
-           "auto_columns_outermost": KERNEL_AUTO | KERNEL_COLUMNS_OUTERMOST,
-           "tma_columns_outermost": KERNEL_TMA | KERNEL_COLUMNS_OUTERMOST,
-           "tma_staged_columns_outermost": KERNEL_TMA_STAGED | KERNEL_COLUMNS_OUTERMOST}
+KERNELS = {"auto": KERNEL_AUTO, "direct": KERNEL_DIRECT, "tma": KERNEL_TMA, "tma_staged": KERNEL_TMA_STAGED}
 
 # every symbol include/shrimpy_b200.h declares; tests check the library exports all of them
 EXPORTS = (

@@ -45,7 +45,6 @@ struct DeskewParams {
     int nz_cap;    // scan slices per staged row (multiple of 8, <= 256)
     int tiles_x;   // number of raw-x tiles
     int tiles_o2;  // number of o2 tiles
-    int cols_outer;  // block order: 0 = (x tile, o2 tile) fastest, tilt block outermost; 1 = o2 tile outermost (SHRIMPY_KERNEL_COLUMNS_OUTERMOST)
 };
 
 // Arithmetic shared by every kernel in this file (so that they agree bit for bit):
@@ -309,8 +308,8 @@ __global__ void __launch_bounds__(kTmaThreads, 4)
 
     // raw-x tile fastest: CTAs that run together read adjacent 128-byte segments of the same DRAM rows
     // (measured: the alternative order makes no difference on B200)
-    const int tx = P.cols_outer ? blockIdx.x : blockIdx.x % P.tiles_x;
-    const int t2 = P.cols_outer ? blockIdx.z : blockIdx.x / P.tiles_x;
+    const int tx = blockIdx.x % P.tiles_x;
+    const int t2 = blockIdx.x / P.tiles_x;
     const int p = P.p0 + blockIdx.y;
     const int x0 = tx * TX;
     const int c0 = P.cbeg + t2 * P.T2;
@@ -532,8 +531,8 @@ __global__ void __launch_bounds__(kTmaThreads, NAVG <= 2 ? 4 : 3)
     const uint32_t region_bytes = (uint32_t)P.nz_cap * kRowBytes;
     float *stage = reinterpret_cast<float *>(smem_dyn + pad + NAVG * region_bytes);   // 2 x EPC x kStagePitch floats
 
-    const int tx = P.cols_outer ? blockIdx.x : blockIdx.x % P.tiles_x;
-    const int t2 = P.cols_outer ? blockIdx.z : blockIdx.x / P.tiles_x;
+    const int tx = blockIdx.x % P.tiles_x;
+    const int t2 = blockIdx.x / P.tiles_x;
     const int p = P.p0 + blockIdx.y;
     const int x0 = tx * TX;
     const int c0 = P.cbeg + t2 * T2;
@@ -749,17 +748,12 @@ static int launch_direct(const DeskewParams &Pin, cudaStream_t stream) {
     return SHRIMPY_OK;
 }
 
-static dim3 tma_grid(const DeskewParams &P) {
-    return P.cols_outer ? dim3((unsigned)P.tiles_x, (unsigned)P.pcount, (unsigned)P.tiles_o2)
-                        : dim3((unsigned)((long long)P.tiles_x * P.tiles_o2), (unsigned)P.pcount);
-}
-
 template <typename T, int NAVG>
 static int launch_tma_staged_n(const CUtensorMap &tmap, const DeskewParams &P, size_t smem, cudaStream_t stream) {
     auto kern = deskew_tma_staged_kernel<T, NAVG>;
     if (smem + 1024 > 48 * 1024)
         SHRIMPY_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<tma_grid(P), kTmaThreads, smem, stream>>>(tmap, P);
+    kern<<<dim3((unsigned)((long long)P.tiles_x * P.tiles_o2), (unsigned)P.pcount), kTmaThreads, smem, stream>>>(tmap, P);
     count_launch();
     SHRIMPY_CUDA_TRY(cudaGetLastError());
     return SHRIMPY_OK;
@@ -771,7 +765,7 @@ static int launch_tma_n(const CUtensorMap &tmap, const DeskewParams &P, size_t s
                         : (P.range ? deskew_tma_kernel<T, NAVG, false, true> : deskew_tma_kernel<T, NAVG, false, false>);
     if (smem + 1024 > 48 * 1024)  // static smem counts against the 48 KB default as well
         SHRIMPY_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<tma_grid(P), kTmaThreads, smem, stream>>>(tmap, P);
+    kern<<<dim3((unsigned)((long long)P.tiles_x * P.tiles_o2), (unsigned)P.pcount), kTmaThreads, smem, stream>>>(tmap, P);
     count_launch();
     SHRIMPY_CUDA_TRY(cudaGetLastError());
     return SHRIMPY_OK;
@@ -822,7 +816,6 @@ static int launch_tma(const DeskewParams &Pin, cudaStream_t stream, bool *used, 
     }
     P.tiles_x = (P.X + TX - 1) / TX;
     P.tiles_o2 = (P.cend - P.cbeg + P.T2 - 1) / P.T2;
-    if (P.cols_outer && P.tiles_o2 > 65535) P.cols_outer = 0;
     if ((long long)P.tiles_x * P.tiles_o2 > 2147483647LL) {
         if (required) return fail(SHRIMPY_EINVAL, "deskew: grid too large");
         return SHRIMPY_OK;
@@ -936,8 +929,6 @@ static int deskew_window_impl(const void *d_raw, int raw_dtype, float *d_out, in
         return fail(SHRIMPY_EINVAL, "deskew: bad shape Z=%d Y=%d X=%d Xp=%d n=%d", Z, Y, X, Xp, n_avg);
     if (raw_dtype != SHRIMPY_U16 && raw_dtype != SHRIMPY_F32)
         return fail(SHRIMPY_EINVAL, "deskew: raw_dtype must be SHRIMPY_U16 or SHRIMPY_F32, got %d", raw_dtype);
-    const int cols_outer = (kernel & SHRIMPY_KERNEL_COLUMNS_OUTERMOST) != 0;
-    kernel &= ~SHRIMPY_KERNEL_COLUMNS_OUTERMOST;
     if (kernel < SHRIMPY_KERNEL_AUTO || kernel > SHRIMPY_KERNEL_TMA_STAGED)
         return fail(SHRIMPY_EINVAL, "deskew: unknown kernel selector %d", kernel);
     if (!std::isfinite(m00) || !std::isfinite(m02) || !std::isfinite(shift))
@@ -979,7 +970,6 @@ static int deskew_window_impl(const void *d_raw, int raw_dtype, float *d_out, in
     P.cval = cval;
     P.inv_n = 1.0f / (float)n_avg;
     P.scale = d_scale;
-    P.cols_outer = cols_outer;
     P.range = reinterpret_cast<unsigned *>(d_range);   // the two result floats double as the ordered-key slots
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (d_range) {

@@ -402,8 +402,7 @@ class PagedStack(PagedWindow):
         self._fds = []
 
 
-def deskew_paged_split(stack, g: DeskewGeometry, shard: PagedShard, *, cval: float = 0.0, window_fn=None,
-                       kernel: str = "auto_columns_outermost"):
+def deskew_paged_split(stack, g: DeskewGeometry, shard: PagedShard, *, cval: float = 0.0, window_fn=None):
     """This rank's output columns ``out[:, :, c0:c1]`` in ONE launch over its window of the paged stack.
 
     ``stack`` needs ``slices(z0, z1)`` (``PagedStack``, or a host stand-in in the CPU tests); ``window_fn`` defaults
@@ -414,10 +413,8 @@ def deskew_paged_split(stack, g: DeskewGeometry, shard: PagedShard, *, cval: flo
         from .deskew import deskew_window
 
         def window_fn(slab, g, p_begin, p_count, c_begin, c_count, y_origin, z_origin, cval):
-            # column tiles outermost: the tiles that read the neighbour's pages (the window's first columns) are all
-            # in flight together at the start of the launch, so NVLink runs at its bandwidth, not at its latency
             return deskew_window(slab, g, p_begin=p_begin, p_count=p_count, c_begin=c_begin, c_count=c_count,
-                                 y_origin=y_origin, z_origin=z_origin, cval=cval, kernel=kernel)
+                                 y_origin=y_origin, z_origin=z_origin, cval=cval)
 
     # (Dispatching the column tiles outermost, so that every tile that reads remote pages is in flight at the start of
     # the launch, was tried on 2 GPUs: 2.56 -> 4.54 ms -- the output writes lose their locality -- and removed;

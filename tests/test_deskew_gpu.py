@@ -400,13 +400,3 @@ def test_two_threads_calling_deskew_data_on_one_gpu(torch, sb):
     with HostPipeline(torch.cuda.current_device()) as shared, ThreadPoolExecutor(4) as pool:
         got = list(pool.map(lambda s: shared.deskew(s, g, 0.0), stacks * 2))
     assert all(np.array_equal(g_, w) for g_, w in zip(got, want * 2))
-
-
-@pytest.mark.parametrize("n,keep", [(1, True), (3, False)])
-def test_column_tiles_outermost_is_only_a_block_order(torch, sb, n, keep):
-    """``SHRIMPY_KERNEL_COLUMNS_OUTERMOST`` (what the paged scan split launches with) changes the order in which the
-    tiles are dispatched, nothing else."""
-    raw = torch.from_numpy(synthetic_stack((700, 14, 192), seed=70)).cuda()
-    want = sb.deskew_zyx(raw, 30.0, 0.39, keep, n, kernel="tma")
-    for kernel in ("auto_columns_outermost", "tma_columns_outermost", "tma_staged_columns_outermost"):
-        assert torch.equal(sb.deskew_zyx(raw, 30.0, 0.39, keep, n, kernel=kernel), want), kernel

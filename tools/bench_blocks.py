@@ -236,9 +236,6 @@ def scan_split_block(dist, rank: int, world: int, local: int, peak_gbs: float, *
             stack.fill_own(slices_of)
             stack.barrier()
             remote = _max_over_ranks(dist, pshards[rank].remote_bytes)
-            record("vmm_columns_innermost", lambda: paged_stack.deskew_paged_split(stack, g, pshards[rank], kernel="auto"),
-                   extra=lambda: {"note": "the same launch with the default block order: the tiles that read remote pages are "
-                                          "~5 % of the resident CTAs at any time, NVLink runs latency-bound"})
             record("vmm", lambda: paged_stack.deskew_paged_split(stack, g, pshards[rank]),
                    extra=lambda: {"remote_mb_mapped_max_rank": round(remote / 1e6, 2), "launches_per_rank": 1,
                                   "data_path": "no exchange step: the neighbours' pages are mapped next to the rank's "
