@@ -115,6 +115,15 @@ __global__ void __launch_bounds__(128) deskew_direct_kernel(const DeskewParams P
 template <typename T>
 struct Chunk;  // 16 bytes of raw x held in a uint4
 
+// 16 bytes of a staged row through a 32-bit shared-window address.  A tap's address is kept as
+// (tile + row offset + swizzle key): rows are 128 bytes long and 128-byte aligned, so the swizzled chunk position
+// (chunk << 4) ^ key is the low seven bits of that address XOR-ed with (chunk << 4) -- one LOP3 per load.
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+
 __device__ __forceinline__ uint32_t word_of(const uint4 &v, int i) {
     return i == 0 ? v.x : i == 1 ? v.y : i == 2 ? v.z : v.w;
 }
@@ -134,8 +143,7 @@ struct Chunk<uint16_t> {
 
     // All n rows inside: S as an integer sum of the magic words (exact), W as an FMA chain.
     template <int NAVG>
-    static __device__ __forceinline__ void fast(const uint8_t *tile, const uint32_t *off0, const uint32_t *off1,
-                                                const uint32_t *sw0, const uint32_t *sw1, const float *w,
+    static __device__ __forceinline__ void fast(const uint32_t *a0, const uint32_t *a1, const float *w,
                                                 const float *u, uint32_t cbyte, float inv_n, float *out) {
         if constexpr (NAVG >= 4) {
             // four rows per voxel: the scalar sequence keeps fewer values live (measured 3-6 % faster than the packed one)
@@ -143,8 +151,8 @@ struct Chunk<uint16_t> {
             float W[kElems];
 #pragma unroll
             for (int k = 0; k < NAVG; ++k) {
-                const uint4 A = *reinterpret_cast<const uint4 *>(tile + off0[k] + (cbyte ^ sw0[k]));
-                const uint4 B = *reinterpret_cast<const uint4 *>(tile + off1[k] + (cbyte ^ sw1[k]));
+                const uint4 A = lds128(a0[k] ^ cbyte);
+                const uint4 B = lds128(a1[k] ^ cbyte);
 #pragma unroll
                 for (int j = 0; j < kElems; ++j) {
                     const uint32_t am = magic(A, j), bm = magic(B, j);
@@ -171,8 +179,8 @@ struct Chunk<uint16_t> {
             float2 W2[kElems / 2];
 #pragma unroll
             for (int k = 0; k < NAVG; ++k) {
-                const uint4 A = *reinterpret_cast<const uint4 *>(tile + off0[k] + (cbyte ^ sw0[k]));
-                const uint4 B = *reinterpret_cast<const uint4 *>(tile + off1[k] + (cbyte ^ sw1[k]));
+                const uint4 A = lds128(a0[k] ^ cbyte);
+                const uint4 B = lds128(a1[k] ^ cbyte);
 #pragma unroll
                 for (int j = 0; j < kElems; j += 2) {
                     const uint32_t am0 = magic(A, j), am1 = magic(A, j + 1), bm0 = magic(B, j), bm1 = magic(B, j + 1);
@@ -208,8 +216,7 @@ struct Chunk<uint16_t> {
 // flat-field variant of the fast path (all rows inside): g points at this chunk's kElems scale values of row k,
 // already multiplied by 1/n, in shared memory (same address for every lane: broadcast reads)
 template <typename T, int NAVG>
-__device__ __forceinline__ void fast_scaled(const uint8_t *tile, const uint32_t *off0, const uint32_t *off1,
-                                            const uint32_t *sw0, const uint32_t *sw1, const float *w,
+__device__ __forceinline__ void fast_scaled(const uint32_t *a0, const uint32_t *a1, const float *w,
                                             const float *g, int g_row_stride, uint32_t cbyte, float *out);
 
 template <>
@@ -218,15 +225,14 @@ struct Chunk<float> {
     static __device__ __forceinline__ float get(const uint4 &v, int j) { return __uint_as_float(word_of(v, j)); }
 
     template <int NAVG>
-    static __device__ __forceinline__ void fast(const uint8_t *tile, const uint32_t *off0, const uint32_t *off1,
-                                                const uint32_t *sw0, const uint32_t *sw1, const float *w,
+    static __device__ __forceinline__ void fast(const uint32_t *a0, const uint32_t *a1, const float *w,
                                                 const float *u, uint32_t cbyte, float inv_n, float *out) {
         // packed pairs (FADD2 / FFMA2): the same operations and rounding as the scalar sequence of the other kernels
         float2 S2[kElems / 2], W2[kElems / 2], one2[kElems / 2];
 #pragma unroll
         for (int k = 0; k < NAVG; ++k) {
-            const uint4 A = *reinterpret_cast<const uint4 *>(tile + off0[k] + (cbyte ^ sw0[k]));
-            const uint4 B = *reinterpret_cast<const uint4 *>(tile + off1[k] + (cbyte ^ sw1[k]));
+            const uint4 A = lds128(a0[k] ^ cbyte);
+            const uint4 B = lds128(a1[k] ^ cbyte);
 #pragma unroll
             for (int j = 0; j < kElems; j += 2) {
                 const float2 a2 = make_float2(get(A, j), get(A, j + 1)), b2 = make_float2(get(B, j), get(B, j + 1));
@@ -246,14 +252,13 @@ struct Chunk<float> {
 };
 
 template <typename T, int NAVG>
-__device__ __forceinline__ void fast_scaled(const uint8_t *tile, const uint32_t *off0, const uint32_t *off1,
-                                            const uint32_t *sw0, const uint32_t *sw1, const float *w,
+__device__ __forceinline__ void fast_scaled(const uint32_t *a0, const uint32_t *a1, const float *w,
                                             const float *g, int g_row_stride, uint32_t cbyte, float *out) {
     constexpr int EPC = Chunk<T>::kElems;
 #pragma unroll
     for (int k = 0; k < NAVG; ++k) {
-        const uint4 A = *reinterpret_cast<const uint4 *>(tile + off0[k] + (cbyte ^ sw0[k]));
-        const uint4 B = *reinterpret_cast<const uint4 *>(tile + off1[k] + (cbyte ^ sw1[k]));
+        const uint4 A = lds128(a0[k] ^ cbyte);
+        const uint4 B = lds128(a1[k] ^ cbyte);
         float gk[EPC];
 #pragma unroll
         for (int j = 0; j < EPC; j += 4) {
@@ -308,9 +313,9 @@ __global__ void __launch_bounds__(kTmaThreads, 4)
 
     // raw-x tile fastest: CTAs that run together read adjacent 128-byte segments of the same DRAM rows
     // (measured: the alternative order makes no difference on B200)
-    const int tx = blockIdx.x % P.tiles_x;
-    const int t2 = blockIdx.x / P.tiles_x;
-    const int p = P.p0 + blockIdx.y;
+    const int tx = blockIdx.x;   // raw-x tile fastest, then the o2 tile, then the tilt block (no runtime division)
+    const int t2 = blockIdx.y;
+    const int p = P.p0 + blockIdx.z;
     const int x0 = tx * TX;
     const int c0 = P.cbeg + t2 * P.T2;
     const int c_last = min(c0 + P.T2, P.cend) - 1;
@@ -361,15 +366,15 @@ __global__ void __launch_bounds__(kTmaThreads, 4)
     const bool any_need = s_need != 0;
 
     // Per-thread column state while the boxes are in flight.
-    const int warps_o2 = P.T2 >> 5;           // 1, 2, 4 or 8
-    const int parts = 8 / warps_o2;           // how many warps share one o2 span, splitting the x chunks
-    const int part = warp / warps_o2;
-    const int o2 = c0 + (warp % warps_o2) * 32 + lane;
+    const int w2_log2 = 31 - __clz(P.T2 >> 5);   // T2 = 32, 64, 128 or 256 columns: 1, 2, 4 or 8 warps along o2
+    const int parts = 8 >> w2_log2;              // how many warps share one o2 span, splitting the x chunks
+    const int part = warp >> w2_log2;
+    const int o2 = c0 + (warp & ((1 << w2_log2) - 1)) * 32 + lane;
     const bool col_ok = o2 < P.cend;
 
     float w[NAVG], u[NAVG];           // lerp weight, and the same pre-scaled by 1/n
-    uint32_t off0[NAVG], off1[NAVG];  // byte offset of the two tap rows inside the tile
-    uint32_t sw0[NAVG], sw1[NAVG];    // their swizzle keys ((row & 7) << 4)
+    uint32_t a0[NAVG], a1[NAVG];      // shared address of chunk 0 of the two tap rows: tile + row offset + swizzle key
+    const uint32_t tile_s = smem_u32(tile);
     bool inside[NAVG];
 #pragma unroll
     for (int k = 0; k < NAVG; ++k) {
@@ -381,10 +386,8 @@ __global__ void __launch_bounds__(kTmaThreads, 4)
         u[k] = w[k] * P.inv_n;
         const int r0 = min(z0 - zlo, P.nz_cap - 1);
         const int r1 = min(min(z0 + 1, P.Z - 1) - zlo, P.nz_cap - 1);
-        off0[k] = k * region_bytes + (uint32_t)r0 * kRowBytes;
-        off1[k] = k * region_bytes + (uint32_t)r1 * kRowBytes;
-        sw0[k] = ((uint32_t)r0 & 7u) << 4;
-        sw1[k] = ((uint32_t)r1 & 7u) << 4;
+        a0[k] = tile_s + k * region_bytes + (uint32_t)r0 * kRowBytes + (((uint32_t)r0 & 7u) << 4);
+        a1[k] = tile_s + k * region_bytes + (uint32_t)r1 * kRowBytes + (((uint32_t)r1 & 7u) << 4);
     }
 
     if (any_need) mbar_wait(&bar, 0);
@@ -406,8 +409,8 @@ __global__ void __launch_bounds__(kTmaThreads, 4)
     for (int c = part; c < 8; c += parts) {
         float r[EPC];
         if (warp_all_in) {
-            if (SCALED) fast_scaled<T, NAVG>(tile, off0, off1, sw0, sw1, w, s_scale + c * EPC, TX, (uint32_t)c << 4, r);
-            else Chunk<T>::template fast<NAVG>(tile, off0, off1, sw0, sw1, w, u, (uint32_t)c << 4, P.inv_n, r);
+            if (SCALED) fast_scaled<T, NAVG>(a0, a1, w, s_scale + c * EPC, TX, (uint32_t)c << 4, r);
+            else Chunk<T>::template fast<NAVG>(a0, a1, w, u, (uint32_t)c << 4, P.inv_n, r);
         } else if (warp_none_in) {
 #pragma unroll
             for (int j = 0; j < EPC; ++j) r[j] = P.cval;
@@ -418,8 +421,8 @@ __global__ void __launch_bounds__(kTmaThreads, 4)
             for (int k = 0; k < NAVG; ++k) {
                 uint4 A = make_uint4(0, 0, 0, 0), B = A;
                 if (inside[k]) {
-                    A = *reinterpret_cast<const uint4 *>(tile + off0[k] + (((uint32_t)c << 4) ^ sw0[k]));
-                    B = *reinterpret_cast<const uint4 *>(tile + off1[k] + (((uint32_t)c << 4) ^ sw1[k]));
+                    A = lds128(a0[k] ^ ((uint32_t)c << 4));
+                    B = lds128(a1[k] ^ ((uint32_t)c << 4));
                 }
 #pragma unroll
                 for (int j = 0; j < EPC; ++j) {
@@ -531,9 +534,9 @@ __global__ void __launch_bounds__(kTmaThreads, NAVG <= 2 ? 4 : 3)
     const uint32_t region_bytes = (uint32_t)P.nz_cap * kRowBytes;
     float *stage = reinterpret_cast<float *>(smem_dyn + pad + NAVG * region_bytes);   // 2 x EPC x kStagePitch floats
 
-    const int tx = blockIdx.x % P.tiles_x;
-    const int t2 = blockIdx.x / P.tiles_x;
-    const int p = P.p0 + blockIdx.y;
+    const int tx = blockIdx.x;   // raw-x tile fastest, then the o2 tile, then the tilt block (no runtime division)
+    const int t2 = blockIdx.y;
+    const int p = P.p0 + blockIdx.z;
     const int x0 = tx * TX;
     const int c0 = P.cbeg + t2 * T2;
     const int ncols = min(T2, P.cend - c0);   // columns of this tile that exist
@@ -578,7 +581,8 @@ __global__ void __launch_bounds__(kTmaThreads, NAVG <= 2 ? 4 : 3)
     const bool col_ok = t_local < ncols;
 
     float w[NAVG], u[NAVG];
-    uint32_t off0[NAVG], off1[NAVG], sw0[NAVG], sw1[NAVG];
+    uint32_t a0[NAVG], a1[NAVG];      // shared address of chunk 0 of the two tap rows: tile + row offset + swizzle key
+    const uint32_t tile_s = smem_u32(tile);
     bool inside[NAVG];
 #pragma unroll
     for (int k = 0; k < NAVG; ++k) {
@@ -590,10 +594,8 @@ __global__ void __launch_bounds__(kTmaThreads, NAVG <= 2 ? 4 : 3)
         u[k] = w[k] * P.inv_n;
         const int r0 = min(z0 - zlo, P.nz_cap - 1);
         const int r1 = min(min(z0 + 1, P.Z - 1) - zlo, P.nz_cap - 1);
-        off0[k] = k * region_bytes + (uint32_t)r0 * kRowBytes;
-        off1[k] = k * region_bytes + (uint32_t)r1 * kRowBytes;
-        sw0[k] = ((uint32_t)r0 & 7u) << 4;
-        sw1[k] = ((uint32_t)r1 & 7u) << 4;
+        a0[k] = tile_s + k * region_bytes + (uint32_t)r0 * kRowBytes + (((uint32_t)r0 & 7u) << 4);
+        a1[k] = tile_s + k * region_bytes + (uint32_t)r1 * kRowBytes + (((uint32_t)r1 & 7u) << 4);
     }
 
     // stage geometry (uniform over the CTA): pitch and start offset that make stage index == global float address mod 8
@@ -647,7 +649,7 @@ __global__ void __launch_bounds__(kTmaThreads, NAVG <= 2 ? 4 : 3)
 
     auto compute = [&](int c, float *r) {
         if (warp_all_in) {
-            Chunk<T>::template fast<NAVG>(tile, off0, off1, sw0, sw1, w, u, (uint32_t)c << 4, P.inv_n, r);
+            Chunk<T>::template fast<NAVG>(a0, a1, w, u, (uint32_t)c << 4, P.inv_n, r);
         } else if (warp_none_in) {
 #pragma unroll
             for (int j = 0; j < EPC; ++j) r[j] = P.cval;
@@ -657,8 +659,8 @@ __global__ void __launch_bounds__(kTmaThreads, NAVG <= 2 ? 4 : 3)
             for (int k = 0; k < NAVG; ++k) {
                 uint4 A = make_uint4(0, 0, 0, 0), B = A;
                 if (inside[k]) {
-                    A = *reinterpret_cast<const uint4 *>(tile + off0[k] + (((uint32_t)c << 4) ^ sw0[k]));
-                    B = *reinterpret_cast<const uint4 *>(tile + off1[k] + (((uint32_t)c << 4) ^ sw1[k]));
+                    A = lds128(a0[k] ^ ((uint32_t)c << 4));
+                    B = lds128(a1[k] ^ ((uint32_t)c << 4));
                 }
 #pragma unroll
                 for (int j = 0; j < EPC; ++j) {
@@ -753,7 +755,7 @@ static int launch_tma_staged_n(const CUtensorMap &tmap, const DeskewParams &P, s
     auto kern = deskew_tma_staged_kernel<T, NAVG>;
     if (smem + 1024 > 48 * 1024)
         SHRIMPY_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<dim3((unsigned)((long long)P.tiles_x * P.tiles_o2), (unsigned)P.pcount), kTmaThreads, smem, stream>>>(tmap, P);
+    kern<<<dim3((unsigned)P.tiles_x, (unsigned)P.tiles_o2, (unsigned)P.pcount), kTmaThreads, smem, stream>>>(tmap, P);
     count_launch();
     SHRIMPY_CUDA_TRY(cudaGetLastError());
     return SHRIMPY_OK;
@@ -765,7 +767,7 @@ static int launch_tma_n(const CUtensorMap &tmap, const DeskewParams &P, size_t s
                         : (P.range ? deskew_tma_kernel<T, NAVG, false, true> : deskew_tma_kernel<T, NAVG, false, false>);
     if (smem + 1024 > 48 * 1024)  // static smem counts against the 48 KB default as well
         SHRIMPY_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<dim3((unsigned)((long long)P.tiles_x * P.tiles_o2), (unsigned)P.pcount), kTmaThreads, smem, stream>>>(tmap, P);
+    kern<<<dim3((unsigned)P.tiles_x, (unsigned)P.tiles_o2, (unsigned)P.pcount), kTmaThreads, smem, stream>>>(tmap, P);
     count_launch();
     SHRIMPY_CUDA_TRY(cudaGetLastError());
     return SHRIMPY_OK;
@@ -785,7 +787,7 @@ static int launch_tma(const DeskewParams &Pin, cudaStream_t stream, bool *used, 
     else if ((reinterpret_cast<uintptr_t>(P.raw) & 15u) != 0) why = "raw pointer not 16-byte aligned";
     else if ((P.raw_sy * ES) % 16 != 0 || (P.raw_sz * ES) % 16 != 0) why = "raw strides not multiples of 16 bytes";
     else if (P.raw_sy < P.X || P.raw_sz < (long long)P.y_cnt * P.raw_sy) why = "raw strides overlap";
-    else if (P.pcount > 65535) why = "too many tilt blocks for grid.y";
+    else if (P.pcount > 65535) why = "too many tilt blocks for grid.z";
     else if (staged && (P.scale || P.range)) why = "the staged variant is not built for the fused scale / value range";
 
     if (!why) {
@@ -816,7 +818,7 @@ static int launch_tma(const DeskewParams &Pin, cudaStream_t stream, bool *used, 
     }
     P.tiles_x = (P.X + TX - 1) / TX;
     P.tiles_o2 = (P.cend - P.cbeg + P.T2 - 1) / P.T2;
-    if ((long long)P.tiles_x * P.tiles_o2 > 2147483647LL) {
+    if (P.tiles_o2 > 65535) {
         if (required) return fail(SHRIMPY_EINVAL, "deskew: grid too large");
         return SHRIMPY_OK;
     }
@@ -867,7 +869,9 @@ static int deskew_dispatch(const DeskewParams &P, int kernel, cudaStream_t strea
         // Measured on B200 (profiles/r02_staged_rows_probe.json): the staged variant wins wherever the writes dominate --
         // n = 1: 0.82 -> 0.60 ms, keep_overhang 1.19 -> 0.84 ms, config 5 7.13 -> 5.18 ms (0.92 of the HBM peak), and still
         // 3 % into rows of a whole-sector pitch -- and loses 3-17 % for n >= 2, where the plain kernel stays.
-        bool staged = forced || (kernel == SHRIMPY_KERNEL_AUTO && P.n == 1 && !P.scale && !P.range &&
+        // n = 2 into rows of an odd pitch: 0.410 -> 0.396 ms; into whole-sector rows the plain kernel keeps its 7 % lead.
+        bool staged = forced || (kernel == SHRIMPY_KERNEL_AUTO && !P.scale && !P.range &&
+                                 (P.n == 1 || (P.n == 2 && (P.out_s1 % 8) != 0)) &&
                                  env_int("SHRIMPY_DESKEW_STAGED", 1) != 0);
         int err = launch_tma<T>(P, stream, &used, kernel == SHRIMPY_KERNEL_TMA || forced, staged);
         if (err == SHRIMPY_OK && !used && staged && !forced)      // a 256-column tile does not fit (large r): plain tiles
