@@ -484,7 +484,7 @@ def e2e_block(dist, rank: int, world: int, local: int, raws, outs, params, steps
         s_hand = wall(handover_step, max(2, steps // 2))
         ok_hand = bool(torch.equal(got[0], outs[0]))
     except (RuntimeError, TypeError) as exc:       # a torch build without the uint16 -> float32 copy
-        s_hand, ok_hand = float("nan"), f"{type(exc).__name__}: {exc}"[:200]
+        s_hand, ok_hand = None, f"{type(exc).__name__}: {exc}"[:200]
     got.clear()
     torch.cuda.empty_cache()
 
@@ -508,7 +508,7 @@ def e2e_block(dist, rank: int, world: int, local: int, raws, outs, params, steps
                    "d2h_bytes_per_step": 0, "matches_device_path": ok_online,
                    "what": "uint16 pinned stack -> device -> fast_deskew_zyx, result left on the device "
                            "(preprocessing.py:316 -> :408-413 with the convert fused into the kernel)"},
-        "online_reference_handover": {"value": value(s_hand), "ms_per_step": 1e3 * s_hand,
+        "online_reference_handover": {"value": value(s_hand) if s_hand else None, "ms_per_step": 1e3 * s_hand if s_hand else None,
                                       "h2d_bytes_per_step": 2 * h2d_bytes, "d2h_bytes_per_step": 0,
                                       "matches_device_path": ok_hand,
                                       "what": "the reference's literal hand-over: torch.as_tensor(pageable uint16, device, "
