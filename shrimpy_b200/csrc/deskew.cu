@@ -695,14 +695,15 @@ __global__ void __launch_bounds__(kTmaThreads, NAVG <= 2 ? 4 : 3)
         for (int ps = 0; ps < PASSES; ++ps) {
             float *grow = d_row - (long long)(ps * 4) * P.out_s1;
             if (xc + ps * 4 + drow < P.X) {
-                const int t = PAR == 1 ? d_col[0][ps] : d_col[par][ps];
+                // (selects, not a runtime index: the tables stay in registers)
+                const int t = (PAR == 2 && par) ? d_col[PAR - 1][ps] : d_col[0][ps];
                 if (t >= 0) {
-                    const float4 v = *reinterpret_cast<const float4 *>(buf + (PAR == 1 ? d_src[0][ps] : d_src[par][ps]));
+                    const float4 v = *reinterpret_cast<const float4 *>(buf + ((PAR == 2 && par) ? d_src[PAR - 1][ps] : d_src[0][ps]));
                     __stcs(reinterpret_cast<float4 *>(grow + t), v);
                 }
                 if (dk < 19) {           // the first warp of a row also carries its ragged ends
-                    const int e = PAR == 1 ? d_rag[0][ps] : d_rag[par][ps];
-                    if (e >= 0) __stcs(grow + e, reinterpret_cast<const float *>(buf)[(PAR == 1 ? d_s0[0][ps] : d_s0[par][ps]) + e]);
+                    const int e = (PAR == 2 && par) ? d_rag[PAR - 1][ps] : d_rag[0][ps];
+                    if (e >= 0) __stcs(grow + e, reinterpret_cast<const float *>(buf)[((PAR == 2 && par) ? d_s0[PAR - 1][ps] : d_s0[0][ps]) + e]);
                 }
             }
         }
