@@ -84,14 +84,50 @@ static int host_threads() {
     return n;
 }
 
-// rows x width bytes, row r from src + r * src_pitch to dst + r * dst_pitch, cut over the host threads by bytes
-static void parallel_copy_rows(char *dst, size_t dst_pitch, const char *src, size_t src_pitch, size_t width,
-                               size_t rows) {
-    const size_t total = width * rows;
-    int T = host_threads();
-    if (total < ((size_t)4 << 20)) T = 1;
-    auto work = [=](int t) {
-        // thread t takes the byte range [t, t+1) * total / T of the row-major payload
+// A few persistent host threads that copy byte ranges (spawning threads per slab cost ~5 ms of a 30 ms call).
+// One pool per process, created on first use; jobs are issued by one caller at a time (the pool has its own mutex).
+class CopyPool {
+  public:
+    // two pools: the gather of the next input slab and the scatter of a finished output slab run side by side
+    static CopyPool &get(int which) {
+        static CopyPool gather(host_threads()), scatter(host_threads());
+        return which == 0 ? gather : scatter;
+    }
+    // rows x width bytes, row r from src + r * src_pitch to dst + r * dst_pitch, cut over the threads by bytes
+    void copy_rows(char *dst, size_t dst_pitch, const char *src, size_t src_pitch, size_t width, size_t rows) {
+        const size_t total = width * rows;
+        if (total < ((size_t)4 << 20) || workers_.empty()) {
+            run_part(dst, dst_pitch, src, src_pitch, width, total, 0, 1);
+            return;
+        }
+        std::lock_guard<std::mutex> one_job(issue_);
+        {
+            std::lock_guard<std::mutex> lock(m_);
+            dst_ = dst; dst_pitch_ = dst_pitch; src_ = src; src_pitch_ = src_pitch; width_ = width; total_ = total;
+            pending_ = (int)workers_.size();
+            ++generation_;
+        }
+        cv_.notify_all();
+        run_part(dst, dst_pitch, src, src_pitch, width, total, 0, (int)workers_.size() + 1);
+        std::unique_lock<std::mutex> lock(m_);
+        done_.wait(lock, [&] { return pending_ == 0; });
+    }
+
+  private:
+    explicit CopyPool(int threads) {
+        for (int t = 1; t < threads; ++t) workers_.emplace_back([this, t] { loop(t); });
+    }
+    ~CopyPool() {
+        {
+            std::lock_guard<std::mutex> lock(m_);
+            stop_ = true;
+        }
+        cv_.notify_all();
+        for (auto &w : workers_) w.join();
+    }
+    static void run_part(char *dst, size_t dst_pitch, const char *src, size_t src_pitch, size_t width, size_t total, int t,
+                         int T) {
+        // part t takes the byte range [t, t+1) * total / T of the row-major payload
         size_t a = total / T * t, b = (t == T - 1) ? total : total / T * (t + 1);
         while (a < b) {
             const size_t r = a / width, off = a - r * width;
@@ -99,16 +135,36 @@ static void parallel_copy_rows(char *dst, size_t dst_pitch, const char *src, siz
             memcpy(dst + r * dst_pitch + off, src + r * src_pitch + off, len);
             a += len;
         }
-    };
-    if (T == 1) {
-        work(0);
-        return;
     }
-    std::vector<std::thread> pool;
-    pool.reserve(T - 1);
-    for (int t = 1; t < T; ++t) pool.emplace_back(work, t);
-    work(0);
-    for (auto &th : pool) th.join();
+    void loop(int t) {
+        uint64_t seen = 0;
+        for (;;) {
+            std::unique_lock<std::mutex> lock(m_);
+            cv_.wait(lock, [&] { return stop_ || generation_ != seen; });
+            if (stop_) return;
+            seen = generation_;
+            char *dst = dst_; const char *src = src_;
+            const size_t dp = dst_pitch_, sp = src_pitch_, w = width_, total = total_;
+            const int T = (int)workers_.size() + 1;
+            lock.unlock();
+            run_part(dst, dp, src, sp, w, total, t, T);
+            lock.lock();
+            if (--pending_ == 0) done_.notify_all();
+        }
+    }
+    std::vector<std::thread> workers_;
+    std::mutex m_, issue_;
+    std::condition_variable cv_, done_;
+    uint64_t generation_ = 0;
+    int pending_ = 0;
+    bool stop_ = false;
+    char *dst_ = nullptr; const char *src_ = nullptr;
+    size_t dst_pitch_ = 0, src_pitch_ = 0, width_ = 0, total_ = 0;
+};
+
+static void parallel_copy_rows(int pool, char *dst, size_t dst_pitch, const char *src, size_t src_pitch, size_t width,
+                               size_t rows) {
+    CopyPool::get(pool).copy_rows(dst, dst_pitch, src, src_pitch, width, rows);
 }
 
 static bool is_pageable(const void *ptr) {
@@ -211,7 +267,7 @@ struct OutDrain {
                 const int b = i % shrimpy_pipeline::kBuf;
                 const cudaError_t e = cudaEventSynchronize(p->ev_d2h[b]);   // recorded for slab i before it was enqueued
                 if (e == cudaSuccess)
-                    parallel_copy_rows(reinterpret_cast<char *>(jobs[i].first), jobs[i].second,
+                    parallel_copy_rows(1, reinterpret_cast<char *>(jobs[i].first), jobs[i].second,
                                        reinterpret_cast<const char *>(p->h_stage_out[b]), jobs[i].second,
                                        jobs[i].second, 1);
                 {
@@ -317,7 +373,7 @@ static int deskew_host_locked(shrimpy_pipeline *p, const void *h_raw, int raw_dt
         if (stage_in) {
             // gather the slab into the ring on the host threads (the H2D of slab i - kBuf has left this slot) ...
             if (i >= kBuf) SHRIMPY_CUDA_TRY(cudaEventSynchronize(p->ev_h2d[b]));
-            parallel_copy_rows(static_cast<char *>(p->h_stage_in[b]), width, src, src_pitch, width, (size_t)Z);
+            parallel_copy_rows(0, static_cast<char *>(p->h_stage_in[b]), width, src, src_pitch, width, (size_t)Z);
             p->staged_in_bytes += (int64_t)(width * Z);
         }
         if (i >= kBuf) SHRIMPY_CUDA_TRY(cudaStreamWaitEvent(p->s_h2d, p->ev_run[b], 0));  // slab i-kBuf consumed
