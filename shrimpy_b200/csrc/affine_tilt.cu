@@ -231,8 +231,9 @@ __global__ void __launch_bounds__(tilt_threads(SWAP), (IA * RB <= 4) ? 3 : 2)
                 for (int seq = 0; seq < nseq; ++seq) {
                     const unsigned slot = (unsigned)(zstart + dir * seq) & mask;
                     const int round = seq >> ring_log2;
-                    if (round > 0)
-                        while (!mbar_try_wait_s(empty_s + 8u * slot, (round - 1) & 1)) __nanosleep(300);
+                    // suspended by the hardware until the slot is handed back (a try_wait / nanosleep(300) spin was
+                    // 75 M of the general case's 607 M issued warp instructions: profiles/r02_ncu_path.txt, source page)
+                    if (round > 0) mbar_wait_suspend_s(empty_s + 8u * slot, (round - 1) & 1, 4000u);
                     load_plane(seq);
                 }
             }

@@ -510,6 +510,9 @@ def _map_file(path) -> np.ndarray:
 
 
 def _pread_piece(path, offset: int, dest: memoryview) -> int:
+    # (Copying out of a memory map instead -- 6 GB/s per thread against 3-4 GB/s here for one thread -- was measured on
+    # a B200 box with 14 loader threads: 8.0 -> 4.6 GVoxel/s for the plate; the threads serialise on the address
+    # space's lock while mapping.  preadv stays.)
     fd = os.open(path, os.O_RDONLY)
     try:
         done = 0
