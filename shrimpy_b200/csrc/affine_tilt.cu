@@ -123,7 +123,10 @@ __global__ void __launch_bounds__(tilt_threads(SWAP), (IA * RB <= 4) ? 3 : 2)
     __shared__ __align__(16) StepCoarse coarse[kTiltMaxSteps];
     __shared__ int s_zmin, s_zmax;
     float *ring = smem_raw + (((128u - (smem_u32(smem_raw) & 127u)) & 127u) >> 2);
-    const uint32_t full_s = smem_u32(full), empty_s = smem_u32(empty), ring_s = smem_u32(ring);
+    uint32_t full_s = smem_u32(full), empty_s = smem_u32(empty), ring_s = smem_u32(ring), tab_s = smem_u32(tab);
+    // Opaque to the compiler from here on: otherwise every use in the march re-derives the shared window base
+    // (S2R SR_CgaCtaId + MOV + LEA, a ~25-cycle special-register read on the critical path of every step).
+    asm volatile("" : "+r"(full_s), "+r"(empty_s), "+r"(ring_s), "+r"(tab_s));
 
     const int ring_log2 = P.ring_log2, mask = (1 << ring_log2) - 1;
     const int pitch = P.pitch;
@@ -278,7 +281,8 @@ __global__ void __launch_bounds__(tilt_threads(SWAP), (IA * RB <= 4) ? 3 : 2)
     unsigned eslot = rslot;                        // slot of plane `released`
 
     for (int lz = 0; lz < nsteps; ++lz, pcol += plane, pstep += plane, pdrain += plane) {
-        const StepInfo e = tab[lz];
+        StepInfo e;
+        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(e.bz), "=r"(e.by), "=r"(e.bx), "=r"(e.ctl) : "r"(tab_s + 16u * (unsigned)lz));
         const unsigned need = e.ctl & 0xfffu, rel = (e.ctl >> 12) & 0xfffu, cls = e.ctl >> 24;
 #pragma unroll 1
         while (released < rel) {
