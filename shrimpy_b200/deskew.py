@@ -384,8 +384,8 @@ def _pipeline_for(index: int) -> HostPipeline:
     with _pipelines_lock:
         pipe = _pipelines.get(key)
         if pipe is None:
-            dead = {t.ident for t in threading.enumerate()}
-            for k in [k for k in _pipelines if k[1] not in dead]:      # threads that have ended: free their device slabs
+            alive = {t.ident for t in threading.enumerate()}
+            for k in [k for k in _pipelines if k[1] not in alive]:     # threads that have ended: free their device slabs
                 _pipelines.pop(k).close()
             pipe = _pipelines[key] = HostPipeline(index)
     return pipe
