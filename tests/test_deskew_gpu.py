@@ -400,3 +400,38 @@ def test_two_threads_calling_deskew_data_on_one_gpu(torch, sb):
     with HostPipeline(torch.cuda.current_device()) as shared, ThreadPoolExecutor(4) as pool:
         got = list(pool.map(lambda s: shared.deskew(s, g, 0.0), stacks * 2))
     assert all(np.array_equal(g_, w) for g_, w in zip(got, want * 2))
+
+
+def test_random_geometries_every_kernel_agrees_bitwise(torch, sb):
+    """40 seeded random stacks (ragged X tiles, Y % n != 0, windows, both dtypes, angles 10..45, ratios 0.2..0.9):
+    direct == plain TMA == staged TMA == AUTO, bit for bit, and the result equals the C oracle to 2e-6 of range."""
+    from oracle import c_oracle
+    from shrimpy_b200._cabi import ShrimpyB200Error
+
+    rng = np.random.default_rng(2024)
+    refused = 0
+    for case in range(40):
+        Z, Y = int(rng.integers(40, 400)), int(rng.integers(1, 14))
+        X = int(rng.integers(1, 40)) * 8                        # TMA rows want 16-byte multiples
+        ang, r = round(float(rng.uniform(10, 45)), 2), round(float(rng.uniform(0.2, 0.9)), 3)
+        keep, n = bool(rng.integers(0, 2)), int(rng.integers(1, 5))
+        dtype = np.uint16 if case % 3 else np.float32
+        raw_np = synthetic_stack((Z, Y, X), seed=100 + case, dtype=dtype)
+        g = sb.deskew_geometry((Z, Y, X), ang, r, keep, n)
+        if g.out_shape[2] == 0:
+            continue
+        raw = torch.from_numpy(raw_np).cuda()
+        want = sb.deskew_zyx(raw, ang, r, keep, n, kernel="direct")
+        for kernel in ("tma", "tma_staged", "auto"):
+            try:
+                got = sb.deskew_zyx(raw, ang, r, keep, n, kernel=kernel)
+            except ShrimpyB200Error as exc:       # forced staged tiles that do not fit shared memory are refused, by name
+                assert kernel == "tma_staged" and "too large" in str(exc), (case, kernel, str(exc))
+                refused += 1
+                continue
+            assert torch.equal(got, want), (case, kernel, (Z, Y, X), ang, r, keep, n, dtype)
+        if case % 8 == 0:
+            ref = c_oracle.deskew_data(raw_np, ang, r, keep, n)
+            assert np.array_equal(want.cpu().numpy() == 0.0, ref == 0.0)
+            assert_close_range(want.cpu().numpy(), ref, TIGHT_TOL, f"case {case}")
+    assert refused < 20
