@@ -73,6 +73,24 @@ def _timed(dist, fn, reps: int):
     return sorted(times)[len(times) // 2], last
 
 
+def _nvlink_rx_bytes(local: int):
+    """Cumulative NVLink payload bytes RECEIVED by this GPU over all its links (NVML field
+    NVLINK_THROUGHPUT_DATA_RX, KiB), or None when the driver does not expose it.  A hardware counter outside our code:
+    the evidence that a kernel's loads of mapped neighbour pages really travel over NVLink."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        vis = [v for v in os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",") if v.strip().isdigit()]
+        handle = pynvml.nvmlDeviceGetHandleByIndex(int(vis[local]) if local < len(vis) else local)
+        vals = pynvml.nvmlDeviceGetFieldValues(handle, [(pynvml.NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_RX, 0xFFFFFFFF)])
+        if vals[0].nvmlReturn != 0:
+            return None
+        return int(vals[0].value.ullVal) * 1024
+    except Exception:
+        return None
+
+
 # --------------------------------------------------------------------------------------------------
 # config 5: one oversized volume split along the scan axis
 # --------------------------------------------------------------------------------------------------
@@ -123,13 +141,20 @@ def scan_split_block(dist, rank: int, world: int, local: int, peak_gbs: float, *
     def record(name, run, extra=None, close=None):
         try:
             run()                                    # warm-up (NCCL channels, first mappings)
+            torch.cuda.synchronize()
+            rx0 = _nvlink_rx_bytes(local)
             ms, piece = _timed(dist, run, reps)
+            rx1 = _nvlink_rx_bytes(local)
             ok = None if ref is None else _all_true(dist, torch.equal(piece, ref))
             del piece
             entry = {"ms": round(ms, 4), "algorithmic_gbs_total": round(alg_bytes / ms / 1e6, 1),
                      "algorithmic_gbs_per_gpu": round(alg_bytes / world / ms / 1e6, 1),
                      "frac_of_hbm_peak_per_gpu": round(alg_bytes / world / ms / 1e6 / peak_gbs, 4),
                      "bit_equal_to_single_gpu_window": ok}
+            if rx0 is not None and rx1 is not None:
+                # max over ranks of what this GPU RECEIVED over NVLink per launch, by the driver's link counters
+                # (includes the few KiB of the barrier / timing all-reduces between the repetitions)
+                entry["nvlink_rx_mb_per_launch_max_rank_nvml"] = round(_max_over_ranks(dist, (rx1 - rx0) / reps) / 1e6, 2)
             if extra:
                 entry.update(extra())
             res["transports"][name] = entry
