@@ -435,3 +435,13 @@ def test_random_geometries_every_kernel_agrees_bitwise(torch, sb):
             assert np.array_equal(want.cpu().numpy() == 0.0, ref == 0.0)
             assert_close_range(want.cpu().numpy(), ref, TIGHT_TOL, f"case {case}")
     assert refused < 20
+
+
+@pytest.mark.parametrize("n,keep", [(1, True), (1, False), (2, False)])
+def test_host_pipeline_with_the_staged_kernel(torch, sb, n, keep):
+    """``deskew_data`` cuts the stack into tilt slabs and launches window calls: with average_n_slices 1 or 2 those
+    run the staged kernel (AUTO) on slabs with a tilt origin -- same volume as the one-launch device path."""
+    raw = synthetic_stack((220, 37, 256), seed=80 + n)
+    dev = sb.deskew_zyx(torch.from_numpy(raw).cuda(), 30.0, 0.39, keep, n, kernel="tma").cpu().numpy()
+    host = sb.deskew_data(raw, 30.0, 0.39, keep, n)
+    assert np.array_equal(host, dev)
