@@ -230,6 +230,11 @@ int shrimpy_deskew_host(shrimpy_pipeline *p, const void *h_raw, int raw_dtype, f
 int shrimpy_pipeline_stats(const shrimpy_pipeline *p, int64_t *launches, int64_t *h2d_bytes, int64_t *d2h_bytes);
 /* bytes of the last call that went through the pipeline's own page-locked staging rings (pageable h_raw / h_out) */
 int shrimpy_pipeline_staged_bytes(const shrimpy_pipeline *p, int64_t *in_bytes, int64_t *out_bytes);
+/* Page-locked host memory of exactly `bytes` bytes (cudaHostAlloc, portable) and its release: what the Python host
+ * returns the result of deskew_data in when the caller gives no `out` (scripts/measure_psf.py:239-246 takes what the
+ * call returns), so that the device-to-host copies of the pipeline run asynchronously at the PCIe rate. */
+int shrimpy_host_alloc(size_t bytes, void **out);
+int shrimpy_host_free(void *ptr);
 
 /*
  * Blosc-1 frame codec for the OME-Zarr chunk loader (host memory only; no CUDA call).  The reference acquires with

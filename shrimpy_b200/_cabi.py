@@ -45,6 +45,8 @@ EXPORTS = (
     "shrimpy_deskew_host",
     "shrimpy_pipeline_stats",
     "shrimpy_pipeline_staged_bytes",
+    "shrimpy_host_alloc",
+    "shrimpy_host_free",
     "shrimpy_blosc_info",
     "shrimpy_blosc_decode",
     "shrimpy_blosc_encode_bound",
@@ -138,6 +140,10 @@ def _declare(lib) -> None:
     lib.shrimpy_pipeline_stats.argtypes = [c_vp, ctypes.POINTER(c_i64), ctypes.POINTER(c_i64), ctypes.POINTER(c_i64)]
     lib.shrimpy_pipeline_staged_bytes.restype = c_int
     lib.shrimpy_pipeline_staged_bytes.argtypes = [c_vp, ctypes.POINTER(c_i64), ctypes.POINTER(c_i64)]
+    lib.shrimpy_host_alloc.restype = c_int
+    lib.shrimpy_host_alloc.argtypes = [ctypes.c_size_t, ctypes.POINTER(c_vp)]
+    lib.shrimpy_host_free.restype = c_int
+    lib.shrimpy_host_free.argtypes = [c_vp]
     c_sz, c_i32 = ctypes.c_size_t, ctypes.c_int32
     lib.shrimpy_blosc_info.restype = c_int
     lib.shrimpy_blosc_info.argtypes = [c_vp, c_sz, ctypes.POINTER(c_i64), ctypes.POINTER(c_i64), ctypes.POINTER(c_i32),

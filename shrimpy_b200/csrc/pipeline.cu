@@ -176,6 +176,21 @@ static bool is_pageable(const void *ptr) {
     return attr.type == cudaMemoryTypeUnregistered;
 }
 
+// Page-locked host memory of exactly the size asked for (the host side keeps its own small cache of result blocks: a
+// general-purpose caching allocator rounds 1.05 GB up to 2 GiB, and page-locking is what a cold call waits for).
+extern "C" int shrimpy_host_alloc(size_t bytes, void **out) {
+    if (!out || bytes == 0) return fail(SHRIMPY_EINVAL, "host_alloc: bad arguments");
+    *out = nullptr;
+    SHRIMPY_CUDA_TRY(cudaHostAlloc(out, bytes, cudaHostAllocPortable));
+    return SHRIMPY_OK;
+}
+
+extern "C" int shrimpy_host_free(void *ptr) {
+    if (!ptr) return SHRIMPY_OK;
+    SHRIMPY_CUDA_TRY(cudaFreeHost(ptr));
+    return SHRIMPY_OK;
+}
+
 extern "C" int shrimpy_pipeline_create(int device, size_t device_bytes_budget, shrimpy_pipeline **out) {
     if (!out) return fail(SHRIMPY_EINVAL, "pipeline_create: null out");
     int count = 0;

@@ -22,7 +22,6 @@ import ctypes
 import math
 import os
 import threading
-import weakref
 from dataclasses import dataclass
 from typing import Optional, Sequence, Tuple, Union
 
@@ -418,44 +417,77 @@ def deskew_data(raw_data: np.ndarray, ls_angle_deg: float, px_to_scan_ratio: flo
     return _pipeline_for(dev.index).deskew(raw, g, fill, out)
 
 
-_pinned_lock = threading.Lock()
-_pinned_live = 0        # bytes of page-locked results currently held by callers
+class _PinnedBlock:
+    """One page-locked block handed out as the base object of a result array; returns itself to the pool when the
+    caller drops the array."""
+
+    def __init__(self, ptr: int, nbytes: int, shape):
+        self.ptr, self.nbytes = ptr, nbytes
+        self.__array_interface__ = {"shape": tuple(int(v) for v in shape), "typestr": "<f4", "data": (ptr, False),
+                                    "version": 3}
+
+    def __del__(self):
+        try:
+            _pinned_pool.give_back(self.ptr, self.nbytes)
+        except Exception:       # interpreter shutdown: the library or the pool may be gone already
+            pass
 
 
-def _pinned_budget() -> int:
-    return int(os.environ.get("SHRIMPY_PINNED_RESULT_BYTES", 4 << 30))
+class _PinnedPool:
+    """Page-locked result blocks of exactly the sizes asked for, cached by size.  Live and cached blocks together
+    never exceed ``SHRIMPY_PINNED_RESULT_BYTES`` (default 4 GiB): page-locking new memory is slow (hundreds of ms per
+    GB), so a loop that consumes each result pins once and reuses the block, and a caller that keeps every result
+    (``scripts/measure_psf.py:239-249`` collects the chunks in a list) gets ordinary arrays, filled through the
+    pipeline's staging ring, for whatever does not fit."""
+
+    def __init__(self):
+        self.lock = threading.Lock()
+        self.free: dict = {}            # nbytes -> [ptr, ...]
+        self.total = 0                  # bytes page-locked through this pool, live + cached
+
+    @staticmethod
+    def budget() -> int:
+        return int(os.environ.get("SHRIMPY_PINNED_RESULT_BYTES", 4 << 30))
+
+    def take(self, shape) -> Optional[np.ndarray]:
+        nbytes = 4 * int(np.prod(shape))
+        with self.lock:
+            cached = self.free.get(nbytes)
+            ptr = cached.pop() if cached else None
+            if ptr is None:
+                # make room by releasing cached blocks of other sizes before giving up
+                while self.total + nbytes > self.budget() and any(self.free.values()):
+                    size = next(k for k, v in self.free.items() if v)
+                    _cabi.lib().shrimpy_host_free(ctypes.c_void_p(self.free[size].pop()))
+                    self.total -= size
+                if self.total + nbytes > self.budget():
+                    return None
+                self.total += nbytes
+        if ptr is None:
+            out = ctypes.c_void_p()
+            if _cabi.lib().shrimpy_host_alloc(nbytes, ctypes.byref(out)) != _cabi.OK or not out.value:
+                with self.lock:
+                    self.total -= nbytes
+                return None                 # the host refuses to lock that much: an ordinary array will do
+            ptr = int(out.value)
+        return np.asarray(_PinnedBlock(ptr, nbytes, shape))
+
+    def give_back(self, ptr: int, nbytes: int) -> None:
+        with self.lock:
+            self.free.setdefault(nbytes, []).append(ptr)
 
 
-def _pinned_release(nbytes: int) -> None:
-    global _pinned_live
-    with _pinned_lock:
-        _pinned_live -= nbytes
+_pinned_pool = _PinnedPool()
 
 
 def _empty_pinned_result(torch, shape) -> np.ndarray:
-    """Result array of a numpy-in/numpy-out call, taken from torch's caching pinned-host allocator.
+    """Result array of a numpy-in/numpy-out call: an ordinary float32 ndarray over a page-locked block of exactly
+    its size (``shrimpy_host_alloc``), or a pageable one when the pool's budget is spent.
 
     The device-to-host copy is the stage that bounds the host path and it runs at the full PCIe
-    rate straight into page-locked memory (B200: 32 ms per mantis channel against 48 ms through the pipeline's staging
-    ring into a pageable array).  The array is an ordinary float32 ndarray whose base keeps the block alive; when the
-    caller drops it the block returns to torch's cache, so a loop over chunks or positions that consumes each result
-    pins memory once.  Page-locking NEW memory is slow (hundreds of ms per GB), so a caller that keeps every result
-    (``scripts/measure_psf.py:239-249`` collects the chunks in a list) must not pin without bound: at most
-    ``SHRIMPY_PINNED_RESULT_BYTES`` (default 4 GiB) of results are page-locked at a time, the rest are ordinary arrays
-    filled through the staging ring.  Falls back to pageable memory when the host refuses to lock that much.
-    """
-    global _pinned_live
-    nbytes = 4 * int(np.prod(shape))
-    with _pinned_lock:
-        take = _pinned_live + nbytes <= _pinned_budget()
-        if take:
-            _pinned_live += nbytes
-    if not take:
+    rate straight into page-locked memory (B200: 29 ms per mantis channel against 47 ms through the pipeline's staging
+    ring into a pageable array).  When the caller drops the array the block returns to the pool."""
+    if math.prod(shape) == 0:
         return np.empty(shape, dtype=np.float32)
-    try:
-        block = torch.empty(tuple(shape), dtype=torch.float32, pin_memory=True)
-    except RuntimeError:
-        _pinned_release(nbytes)
-        return np.empty(shape, dtype=np.float32)
-    weakref.finalize(block, _pinned_release, nbytes)
-    return block.numpy()
+    out = _pinned_pool.take(shape)
+    return out if out is not None else np.empty(shape, dtype=np.float32)
