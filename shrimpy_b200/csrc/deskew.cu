@@ -313,8 +313,11 @@ __global__ void __launch_bounds__(kTmaThreads, 4)
 
     // raw-x tile fastest: CTAs that run together read adjacent 128-byte segments of the same DRAM rows
     // (measured: the alternative order makes no difference on B200)
-    const int tx = blockIdx.x;   // raw-x tile fastest, then the o2 tile, then the tilt block (no runtime division)
-    const int t2 = blockIdx.y;
+    // block order: pairs of raw-x tiles fastest (they share 256-byte DRAM accesses), then the o2 tiles of a row (their
+    // 1 KB row segments are neighbours in the output), then the remaining x tiles, then the tilt block
+    const int tx = 2 * blockIdx.y + (blockIdx.x & 1);
+    const int t2 = blockIdx.x >> 1;
+    if (tx >= P.tiles_x) return;
     const int p = P.p0 + blockIdx.z;
     const int x0 = tx * TX;
     const int c0 = P.cbeg + t2 * P.T2;
@@ -534,8 +537,11 @@ __global__ void __launch_bounds__(kTmaThreads, NAVG <= 2 ? 4 : 3)
     const uint32_t region_bytes = (uint32_t)P.nz_cap * kRowBytes;
     float *stage = reinterpret_cast<float *>(smem_dyn + pad + NAVG * region_bytes);   // 2 x EPC x kStagePitch floats
 
-    const int tx = blockIdx.x;   // raw-x tile fastest, then the o2 tile, then the tilt block (no runtime division)
-    const int t2 = blockIdx.y;
+    // block order: pairs of raw-x tiles fastest (they share 256-byte DRAM accesses), then the o2 tiles of a row (their
+    // 1 KB row segments are neighbours in the output), then the remaining x tiles, then the tilt block
+    const int tx = 2 * blockIdx.y + (blockIdx.x & 1);
+    const int t2 = blockIdx.x >> 1;
+    if (tx >= P.tiles_x) return;
     const int p = P.p0 + blockIdx.z;
     const int x0 = tx * TX;
     const int c0 = P.cbeg + t2 * T2;
@@ -756,7 +762,7 @@ static int launch_tma_staged_n(const CUtensorMap &tmap, const DeskewParams &P, s
     auto kern = deskew_tma_staged_kernel<T, NAVG>;
     if (smem + 1024 > 48 * 1024)
         SHRIMPY_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<dim3((unsigned)P.tiles_x, (unsigned)P.tiles_o2, (unsigned)P.pcount), kTmaThreads, smem, stream>>>(tmap, P);
+    kern<<<dim3(2u * (unsigned)P.tiles_o2, (unsigned)((P.tiles_x + 1) / 2), (unsigned)P.pcount), kTmaThreads, smem, stream>>>(tmap, P);
     count_launch();
     SHRIMPY_CUDA_TRY(cudaGetLastError());
     return SHRIMPY_OK;
@@ -768,7 +774,7 @@ static int launch_tma_n(const CUtensorMap &tmap, const DeskewParams &P, size_t s
                         : (P.range ? deskew_tma_kernel<T, NAVG, false, true> : deskew_tma_kernel<T, NAVG, false, false>);
     if (smem + 1024 > 48 * 1024)  // static smem counts against the 48 KB default as well
         SHRIMPY_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<dim3((unsigned)P.tiles_x, (unsigned)P.tiles_o2, (unsigned)P.pcount), kTmaThreads, smem, stream>>>(tmap, P);
+    kern<<<dim3(2u * (unsigned)P.tiles_o2, (unsigned)((P.tiles_x + 1) / 2), (unsigned)P.pcount), kTmaThreads, smem, stream>>>(tmap, P);
     count_launch();
     SHRIMPY_CUDA_TRY(cudaGetLastError());
     return SHRIMPY_OK;
@@ -819,7 +825,7 @@ static int launch_tma(const DeskewParams &Pin, cudaStream_t stream, bool *used, 
     }
     P.tiles_x = (P.X + TX - 1) / TX;
     P.tiles_o2 = (P.cend - P.cbeg + P.T2 - 1) / P.T2;
-    if (P.tiles_o2 > 65535) {
+    if (P.tiles_x > 2 * 65535) {
         if (required) return fail(SHRIMPY_EINVAL, "deskew: grid too large");
         return SHRIMPY_OK;
     }
