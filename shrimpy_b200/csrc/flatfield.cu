@@ -132,8 +132,16 @@ __global__ void __launch_bounds__(kMedThreads) median_z_kernel(const T *__restri
                 if (PAIR) {
                     typename Pair<T>::type v[kBatch];
 #pragma unroll
-                    for (int i = 0; i < kBatch; ++i)
-                        v[i] = __ldg(reinterpret_cast<const typename Pair<T>::type *>(col + (long long)(z + i * kSlices) * sz));
+                    for (int i = 0; i < kBatch; ++i) {
+                        const void *src = col + (long long)(z + i * kSlices) * sz;
+                        if constexpr (sizeof(T) == 2) {
+                            unsigned w32;   // 256-byte L2 prefetch: the neighbouring CTA reads the other 128 B of the line pair
+                            asm volatile("ld.global.nc.L2::256B.b32 %0, [%1];" : "=r"(w32) : "l"(src));
+                            memcpy(&v[i], &w32, 4);
+                        } else {
+                            v[i] = __ldg(reinterpret_cast<const typename Pair<T>::type *>(src));
+                        }
+                    }
                     if constexpr (sizeof(T) == 2) {
                         // uint16 pairs stay one 32-bit word: key bytes come out with one PRMT each, both prefixes are
                         // compared through one XOR (the generic path spends 7.5 / 11 instructions per key on this)
